@@ -1,0 +1,287 @@
+"""ctypes binding of include/rsb200.h (librsb200.so).  No torch types cross this boundary;
+torch tensors are passed as raw device pointers (``tensor.data_ptr()``) by the callers."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+HEADER = os.path.join(ROOT, "include", "rsb200.h")
+_LIB_PATH = os.path.join(HERE, "librsb200.so")
+
+KEY_TYPES = {"u32": 0, "i32": 1, "u64": 2, "i64": 3}
+_NP = {"u32": np.uint32, "i32": np.int32, "u64": np.uint64, "i64": np.int64}
+DATASET_KINDS = {"zeros": 0, "range": 1, "inverted": 2, "uniform": 3, "random": 4}
+RS_WITH_PERMUTATION, RS_NO_TMA, RS_NO_PROFILE, RS_NO_KEY_BUFFERS = 0x1, 0x2, 0x4, 0x8
+
+_lib = None
+
+
+class RsError(RuntimeError):
+    def __init__(self, status: int, detail: str):
+        self.status = status
+        super().__init__(f"rsb200: {status_string(status)} ({status}): {detail}")
+
+
+def key_dtype(key_type: str):
+    return np.dtype(_NP[key_type])
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def build_library(verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> radix-sort_b200/librsb200.so (in-tree)."""
+    out = subprocess.run(["make", "-C", os.path.join(HERE, "csrc")], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout, out.stderr)
+    if out.returncode != 0:
+        raise RuntimeError("building librsb200.so failed")
+    return _LIB_PATH
+
+
+def declared_symbols() -> list[str]:
+    """Every function include/rsb200.h declares (used by the CPU test that the library exports them)."""
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rs_[a-z0-9_]+)\s*\(", text)))
+
+
+class _Stat(C.Structure):
+    _fields_ = [("min", C.c_double), ("max", C.c_double), ("avg", C.c_double), ("sum", C.c_double), ("n", C.c_uint64)]
+
+
+class _Runtimes(C.Structure):
+    _fields_ = [("time_histo", _Stat), ("time_scan", _Stat), ("time_reorder", _Stat), ("time_paste", _Stat),
+                ("time_total", _Stat)]
+
+
+def load_library():
+    """Load librsb200.so; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise FileNotFoundError(f"{_LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+    lib = C.CDLL(_LIB_PATH)
+    vp, u64, u32, i = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    sig = {
+        "rs_version": ([], i),
+        "rs_status_string": ([i], C.c_char_p),
+        "rs_last_error_string": ([], C.c_char_p),
+        "rs_device_count": ([C.POINTER(i)], i),
+        "rs_context_create": ([i, C.POINTER(vp)], i),
+        "rs_context_destroy": ([vp], i),
+        "rs_context_sm_count": ([vp, C.POINTER(i)], i),
+        "rs_stream_create": ([vp, C.POINTER(vp)], i),
+        "rs_stream_wrap": ([vp, vp, C.POINTER(vp)], i),
+        "rs_stream_sync": ([vp], i),
+        "rs_stream_destroy": ([vp], i),
+        "rs_host_alloc": ([C.c_size_t, C.POINTER(vp)], i),
+        "rs_host_free": ([vp], i),
+        "rs_round_up_keys": ([u64], u64),
+        "rs_sorter_create": ([vp, i, u64, u32, C.POINTER(vp)], i),
+        "rs_sorter_destroy": ([vp], i),
+        "rs_sorter_pad": ([vp, vp, u64, u64], i),
+        "rs_sorter_upload": ([vp, vp, vp, vp, u64], i),
+        "rs_sorter_sort": ([vp, vp, u64], i),
+        "rs_sorter_download": ([vp, vp, vp, vp, u64], i),
+        "rs_sorter_download_histograms": ([vp, vp, vp, C.c_size_t, C.POINTER(i)], i),
+        "rs_sorter_sort_device": ([vp, vp, vp, vp, vp, vp, vp, vp, u64, i, i, C.POINTER(i)], i),
+        "rs_sorter_runtimes": ([vp, C.POINTER(_Runtimes)], i),
+        "rs_sorter_reset_runtimes": ([vp], i),
+        "rs_sorter_launch_count": ([vp, C.POINTER(u64)], i),
+        "rs_dataset_fill_device": ([vp, vp, i, i, u64, u64, u64, vp, u64], i),
+        "rs_check_device": ([vp, vp, i, vp, u64, C.POINTER(u64 * 4)], i),
+        "rs_check_permutation_device": ([vp, vp, i, vp, vp, vp, u64, C.POINTER(u64 * 2)], i),
+        "rs_lower_bound_device": ([vp, vp, i, vp, u64, vp, u64, vp], i),
+    }
+    for name, (args, res) in sig.items():
+        f = getattr(lib, name)
+        f.argtypes, f.restype = args, res
+    _lib = lib
+    return lib
+
+
+def status_string(status: int) -> str:
+    return load_library().rs_status_string(status).decode()
+
+
+def _check(status: int):
+    if status != 0:
+        raise RsError(status, load_library().rs_last_error_string().decode())
+
+
+def round_up_keys(n: int) -> int:
+    return int(load_library().rs_round_up_keys(n))
+
+
+def _addr(x):
+    """numpy array / HostBuffer / int device pointer / None -> void*"""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data_as(C.c_void_p)
+    if isinstance(x, HostBuffer):
+        return C.c_void_p(x.ptr)
+    return C.c_void_p(int(x))
+
+
+class Context:
+    """CUDA device state; replaces ComputeState (reference Common/ComputeState.cpp:14-104)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.handle = C.c_void_p()
+        _check(self.lib.rs_context_create(device, C.byref(self.handle)))
+        self.device = device
+
+    @staticmethod
+    def device_count() -> int:
+        n = C.c_int(0)
+        load_library().rs_device_count(C.byref(n))
+        return n.value
+
+    @property
+    def sm_count(self) -> int:
+        n = C.c_int(0)
+        _check(self.lib.rs_context_sm_count(self.handle, C.byref(n)))
+        return n.value
+
+    def close(self):
+        if self.handle:
+            self.lib.rs_context_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    # -- device helpers -------------------------------------------------------------------------
+    def fill_dataset(self, stream, key_type, kind, d_out, n, seed=0x5EED, global_offset=0, total_n=None):
+        total_n = n if total_n is None else total_n
+        _check(self.lib.rs_dataset_fill_device(self.handle, stream.handle, KEY_TYPES[key_type], DATASET_KINDS[kind],
+                                               seed, global_offset, total_n, _addr(d_out), n))
+
+    def check(self, stream, key_type, d_keys, n):
+        """-> dict(unordered, sum, hash_sum, hash_xor) computed on the device (blocks)."""
+        res = (C.c_uint64 * 4)()
+        _check(self.lib.rs_check_device(self.handle, stream.handle, KEY_TYPES[key_type], _addr(d_keys), n, C.byref(res)))
+        return {"unordered": res[0], "sum": res[1], "hash_sum": res[2], "hash_xor": res[3]}
+
+    def check_permutation(self, stream, key_type, d_keys_in, d_keys_out, d_perm, n):
+        res = (C.c_uint64 * 2)()
+        _check(self.lib.rs_check_permutation_device(self.handle, stream.handle, KEY_TYPES[key_type], _addr(d_keys_in),
+                                                    _addr(d_keys_out), _addr(d_perm), n, C.byref(res)))
+        return {"mismatches": res[0], "unstable": res[1]}
+
+    def lower_bound(self, stream, key_type, d_keys, n, d_queries, num_queries, d_out):
+        _check(self.lib.rs_lower_bound_device(self.handle, stream.handle, KEY_TYPES[key_type], _addr(d_keys), n,
+                                              _addr(d_queries), num_queries, _addr(d_out)))
+
+
+class Stream:
+    """A CUDA stream: replaces the in-order cl::CommandQueue the reference passes around."""
+
+    def __init__(self, ctx: Context, cuda_stream: int | None = None):
+        self.lib, self.ctx = ctx.lib, ctx
+        self.handle = C.c_void_p()
+        if cuda_stream is None:
+            _check(self.lib.rs_stream_create(ctx.handle, C.byref(self.handle)))
+        else:
+            _check(self.lib.rs_stream_wrap(ctx.handle, C.c_void_p(cuda_stream), C.byref(self.handle)))
+
+    def sync(self):
+        _check(self.lib.rs_stream_sync(self.handle))
+
+    def close(self):
+        if self.handle:
+            self.lib.rs_stream_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+class HostBuffer:
+    """Pinned host memory viewed as a numpy array (upload / download stage)."""
+
+    def __init__(self, n: int, dtype):
+        self.lib = load_library()
+        self.dtype = np.dtype(dtype)
+        p = C.c_void_p()
+        _check(self.lib.rs_host_alloc(max(1, n) * self.dtype.itemsize, C.byref(p)))
+        self.ptr = p.value
+        self.n = n
+        buf = (C.c_char * (max(1, n) * self.dtype.itemsize)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=n)
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            self.lib.rs_host_free(C.c_void_p(self.ptr))
+            self.ptr = 0
+
+
+class Sorter:
+    """Binding of rs_sorter: what RadixSortGPU<T> + ComputeDeviceData<T> are in the reference
+    (src/RadixSortGPU.h:38-124, src/ComputeDeviceData.h:12-28)."""
+
+    def __init__(self, ctx: Context, key_type: str, max_keys: int, flags: int = 0):
+        self.lib, self.ctx, self.key_type = ctx.lib, ctx, key_type
+        self.dtype = key_dtype(key_type)
+        self.max_keys, self.flags = max_keys, flags
+        self.handle = C.c_void_p()
+        _check(self.lib.rs_sorter_create(ctx.handle, KEY_TYPES[key_type], max_keys, flags, C.byref(self.handle)))
+
+    def pad(self, stream, first_key, rounded):
+        _check(self.lib.rs_sorter_pad(self.handle, stream.handle, first_key, rounded))
+
+    def upload(self, stream, h_keys, h_perm=None, n=None):
+        n = len(h_keys) if n is None else n
+        _check(self.lib.rs_sorter_upload(self.handle, stream.handle, _addr(h_keys), _addr(h_perm), n))
+
+    def sort(self, stream, n):
+        _check(self.lib.rs_sorter_sort(self.handle, stream.handle, n))
+
+    def download(self, stream, h_keys_out, h_perm_out=None, n=None):
+        n = len(h_keys_out) if n is None else n
+        _check(self.lib.rs_sorter_download(self.handle, stream.handle, _addr(h_keys_out), _addr(h_perm_out), n))
+
+    def download_histograms(self, stream):
+        buf = np.zeros(8 * 256, dtype=np.uint64)
+        passes = C.c_int(0)
+        _check(self.lib.rs_sorter_download_histograms(self.handle, stream.handle, _addr(buf), buf.size, C.byref(passes)))
+        return buf[: passes.value * 256].reshape(passes.value, 256)
+
+    def sort_device(self, stream, d_in, d_buf0, d_buf1, n, d_vin=None, d_vbuf0=None, d_vbuf1=None, begin_bit=0,
+                    end_bit=None) -> int:
+        """Device-pointer entry; returns the index (0/1) of the buffer that holds the result."""
+        end_bit = self.dtype.itemsize * 8 if end_bit is None else end_bit
+        idx = C.c_int(0)
+        _check(self.lib.rs_sorter_sort_device(self.handle, stream.handle, _addr(d_in), _addr(d_buf0), _addr(d_buf1),
+                                              _addr(d_vin), _addr(d_vbuf0), _addr(d_vbuf1), n, begin_bit, end_bit,
+                                              C.byref(idx)))
+        return idx.value
+
+    def runtimes(self) -> dict:
+        rt = _Runtimes()
+        _check(self.lib.rs_sorter_runtimes(self.handle, C.byref(rt)))
+        out = {}
+        for name, _ in _Runtimes._fields_:
+            st = getattr(rt, name)
+            out[name] = {"min": st.min, "max": st.max, "avg": st.avg, "sum": st.sum, "n": st.n}
+        return out
+
+    def reset_runtimes(self):
+        _check(self.lib.rs_sorter_reset_runtimes(self.handle))
+
+    @property
+    def launch_count(self) -> int:
+        v = C.c_uint64(0)
+        _check(self.lib.rs_sorter_launch_count(self.handle, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if self.handle:
+            self.lib.rs_sorter_destroy(self.handle)
+            self.handle = C.c_void_p()

@@ -1,0 +1,816 @@
+// rs_api.cu -- the C ABI of include/rsb200.h over the CUDA runtime.
+//
+// Host side of the hot path: what RadixSortGPU<T>::{initialize, uploadData, calculate, downloadData,
+// release} (reference src/RadixSortGPU.cpp:451-543, 299-357, 444-449) and ComputeDeviceData<T>
+// (src/ComputeDeviceData.cpp:10-79) do over OpenCL is done here over cudaMalloc'd ping-pong buffers
+// and stream-ordered launches.  No host synchronisation inside a sort: one memset, the histogram
+// kernel, the scan kernel and one onesweep kernel per 8-bit digit are enqueued back to back.
+#include "../../include/rsb200.h"
+#include "rs_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace rsb;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int status, const char* what, cudaError_t e = cudaSuccess) {
+    char buf[512];
+    if (e != cudaSuccess)
+        snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    else
+        snprintf(buf, sizeof buf, "%s", what);
+    g_last_error = buf;
+    return status;
+}
+#define RS_CUDA(expr, status)                                   \
+    do {                                                        \
+        cudaError_t _e = (expr);                                \
+        if (_e != cudaSuccess) return fail((status), #expr, _e); \
+    } while (0)
+
+struct rs_context_s {
+    int device;
+    int sm_count;
+    int max_smem_optin;
+};
+struct rs_stream_s {
+    rs_context   ctx;
+    cudaStream_t st;
+    bool         owned;
+};
+
+struct EventQuad {
+    cudaEvent_t e[4];  // start, after histogram, after scan, after last pass
+};
+
+struct rs_sorter_s {
+    rs_context  ctx;
+    rs_key_type type;
+    uint32_t    flags;
+    uint64_t    max_keys;
+    size_t      key_bytes;
+    bool        is_signed;
+    bool        has_vals;
+    // device memory
+    void*     keys[2];
+    uint32_t* vals[2];
+    unsigned char* scratch;
+    size_t    scratch_bytes;
+    // result of the last rs_sorter_sort
+    int       result_index;
+    uint64_t  last_n;
+    int       last_passes;
+    int       last_chunks;
+    size_t    last_hist_offset;
+    // profiling
+    std::vector<EventQuad> free_events;
+    std::vector<EventQuad> pending;
+    rs_runtimes            rt;
+    uint64_t               launches;
+};
+
+// Statistics::update of the reference (src/Statistics.h:21-31), including the else-if.
+static void stat_update(rs_statistics& s, double v) {
+    s.n++;
+    s.sum += v;
+    s.avg = s.sum / static_cast<double>(s.n);
+    if (v > s.max)
+        s.max = v;
+    else if (v < s.min)
+        s.min = v;
+}
+static void stat_reset(rs_statistics& s) {
+    s.min = std::numeric_limits<double>::infinity();
+    s.max = -std::numeric_limits<double>::infinity();
+    s.avg = 0.0;
+    s.sum = 0.0;
+    s.n   = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tile configurations (per key width / payload) and launch plumbing
+// ------------------------------------------------------------------------------------------------
+template <typename KeyT, bool HAS_VALS>
+struct TileCfg;
+template <> struct TileCfg<uint32_t, false> { static constexpr int THREADS = 512, KPT = 16, MINB = 2; };
+template <> struct TileCfg<uint32_t, true>  { static constexpr int THREADS = 512, KPT = 12, MINB = 2; };
+template <> struct TileCfg<uint64_t, false> { static constexpr int THREADS = 512, KPT = 8,  MINB = 2; };
+template <> struct TileCfg<uint64_t, true>  { static constexpr int THREADS = 512, KPT = 8,  MINB = 2; };
+
+static int tile_keys(size_t key_bytes, bool has_vals) {
+    if (key_bytes == 4) return has_vals ? TileCfg<uint32_t, true>::THREADS * TileCfg<uint32_t, true>::KPT
+                                        : TileCfg<uint32_t, false>::THREADS * TileCfg<uint32_t, false>::KPT;
+    return has_vals ? TileCfg<uint64_t, true>::THREADS * TileCfg<uint64_t, true>::KPT
+                    : TileCfg<uint64_t, false>::THREADS * TileCfg<uint64_t, false>::KPT;
+}
+
+struct Plan {
+    int      tile;
+    uint64_t num_tiles;
+    uint32_t tiles_per_chunk;
+    uint64_t chunk_keys;
+    int      num_chunks;
+    int      passes;
+    // scratch layout (bytes)
+    size_t off_hist, off_ctr, off_status, zero_bytes, off_base, total;
+};
+
+static Plan make_plan(uint64_t n, size_t key_bytes, bool has_vals, int passes) {
+    Plan p{};
+    p.tile            = tile_keys(key_bytes, has_vals);
+    p.num_tiles       = (n + p.tile - 1) / p.tile;
+    p.tiles_per_chunk = static_cast<uint32_t>(CHUNK_MAX_KEYS / p.tile);
+    p.chunk_keys      = static_cast<uint64_t>(p.tiles_per_chunk) * p.tile;
+    p.num_chunks      = static_cast<int>((n + p.chunk_keys - 1) / p.chunk_keys);
+    if (p.num_chunks < 1) p.num_chunks = 1;
+    p.passes          = passes;
+    auto align = [](size_t x) { return (x + 255) & ~static_cast<size_t>(255); };
+    size_t o     = 0;
+    p.off_hist   = o; o = align(o + sizeof(uint64_t) * passes * p.num_chunks * RADIX);
+    p.off_ctr    = o; o = align(o + sizeof(uint32_t) * MAX_PASSES);
+    p.off_status = o; o = align(o + sizeof(uint32_t) * RADIX * p.num_tiles * passes);
+    p.zero_bytes = o;
+    p.off_base   = o; o = align(o + sizeof(uint64_t) * passes * p.num_chunks * RADIX);
+    p.total      = o;
+    return p;
+}
+
+template <typename KeyT, int NPASS>
+static cudaError_t launch_hist_n(int grid, cudaStream_t st, const KeyT* keys, uint64_t n, const Plan& pl,
+                                 unsigned long long* hist, const PassTable& pt) {
+    rs_histogram_kernel<KeyT, NPASS><<<grid, HIST_THREADS, 0, st>>>(keys, n, pl.chunk_keys, pl.num_chunks, hist, pt);
+    return cudaGetLastError();
+}
+template <typename KeyT>
+static cudaError_t launch_hist(int sm_count, cudaStream_t st, const KeyT* keys, uint64_t n, const Plan& pl,
+                               unsigned long long* hist, const PassTable& pt) {
+    const uint64_t vec_per_block = static_cast<uint64_t>(HIST_THREADS) * HIST_VECS * (16 / sizeof(KeyT));
+    uint64_t want = (std::min<uint64_t>(n, pl.chunk_keys) + vec_per_block - 1) / vec_per_block;
+    int grid = static_cast<int>(std::min<uint64_t>(std::max<uint64_t>(want, 1), static_cast<uint64_t>(sm_count) * 4));
+    switch (pt.num_passes) {
+        case 1: return launch_hist_n<KeyT, 1>(grid, st, keys, n, pl, hist, pt);
+        case 2: return launch_hist_n<KeyT, 2>(grid, st, keys, n, pl, hist, pt);
+        case 3: return launch_hist_n<KeyT, 3>(grid, st, keys, n, pl, hist, pt);
+        case 4: return launch_hist_n<KeyT, 4>(grid, st, keys, n, pl, hist, pt);
+        case 5: return launch_hist_n<KeyT, 5>(grid, st, keys, n, pl, hist, pt);
+        case 6: return launch_hist_n<KeyT, 6>(grid, st, keys, n, pl, hist, pt);
+        case 7: return launch_hist_n<KeyT, 7>(grid, st, keys, n, pl, hist, pt);
+        case 8: return launch_hist_n<KeyT, 8>(grid, st, keys, n, pl, hist, pt);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <typename KeyT, bool HAS_VALS>
+static cudaError_t launch_pass(rs_context ctx, cudaStream_t st, const OnesweepArgs<KeyT>& args) {
+    using C = TileCfg<KeyT, HAS_VALS>;
+    using L = OnesweepSmem<KeyT, HAS_VALS, C::THREADS, C::KPT>;
+    auto kern = rs_onesweep_kernel<KeyT, HAS_VALS, C::THREADS, C::KPT, C::MINB>;
+    static thread_local int cached_device = -1;
+    static thread_local int blocks_per_sm = 0;
+    if (cached_device != ctx->device) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::total));
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, C::THREADS, L::total);
+        if (e != cudaSuccess) return e;
+        if (blocks_per_sm < 1) return cudaErrorLaunchOutOfResources;
+        cached_device = ctx->device;
+    }
+    const uint64_t resident = static_cast<uint64_t>(blocks_per_sm) * ctx->sm_count;
+    const int grid = static_cast<int>(std::min<uint64_t>(args.num_tiles, resident));
+    kern<<<grid, C::THREADS, L::total, st>>>(args);
+    return cudaGetLastError();
+}
+
+static PassTable make_pass_table(size_t key_bytes, bool is_signed, int begin_bit, int end_bit) {
+    PassTable pt{};
+    const int key_bits = static_cast<int>(key_bytes) * 8;
+    int p = 0;
+    for (int b = begin_bit; b < end_bit && p < MAX_PASSES; b += RADIX_BITS, ++p) {
+        const int bits = std::min(RADIX_BITS, end_bit - b);
+        pt.d[p].shift  = b;
+        pt.d[p].mask   = (1u << bits) - 1u;
+        pt.d[p].flip   = 0;
+        if (is_signed && key_bits - 1 >= b && key_bits - 1 < b + bits) pt.d[p].flip = 1u << (key_bits - 1 - b);
+    }
+    pt.num_passes = p;
+    return pt;
+}
+
+template <typename KeyT>
+static int sort_typed(rs_sorter s, cudaStream_t st, const KeyT* in, KeyT* buf0, KeyT* buf1, const uint32_t* vin,
+                      uint32_t* vbuf0, uint32_t* vbuf1, uint64_t n, int begin_bit, int end_bit, bool profile,
+                      int* result_index) {
+    const bool has_vals = vin != nullptr;
+    const PassTable pt = make_pass_table(sizeof(KeyT), s->is_signed, begin_bit, end_bit);
+    if (pt.num_passes < 1) return fail(RS_CALCULATION_FAILED, "empty bit range");
+    const Plan pl = make_plan(n, sizeof(KeyT), has_vals, pt.num_passes);
+    if (pl.total > s->scratch_bytes) return fail(RS_CALCULATION_FAILED, "n exceeds the sorter's max_keys (scratch too small)");
+    if (pl.num_tiles >= (1ull << 32)) return fail(RS_CALCULATION_FAILED, "too many tiles");
+
+    EventQuad q{};
+    if (profile) {
+        if (!s->free_events.empty()) {
+            q = s->free_events.back();
+            s->free_events.pop_back();
+        } else {
+            for (auto& e : q.e) RS_CUDA(cudaEventCreate(&e), RS_CALCULATION_FAILED);
+        }
+        RS_CUDA(cudaEventRecord(q.e[0], st), RS_CALCULATION_FAILED);
+    }
+    auto* hist   = reinterpret_cast<unsigned long long*>(s->scratch + pl.off_hist);
+    auto* ctr    = reinterpret_cast<uint32_t*>(s->scratch + pl.off_ctr);
+    auto* status = reinterpret_cast<uint32_t*>(s->scratch + pl.off_status);
+    auto* base   = reinterpret_cast<unsigned long long*>(s->scratch + pl.off_base);
+
+    RS_CUDA(cudaMemsetAsync(s->scratch, 0, pl.zero_bytes, st), RS_CALCULATION_FAILED);
+    RS_CUDA(launch_hist<KeyT>(s->ctx->sm_count, st, in, n, pl, hist, pt), RS_CALCULATION_FAILED);
+    s->launches++;
+    if (profile) RS_CUDA(cudaEventRecord(q.e[1], st), RS_CALCULATION_FAILED);
+    rs_scan_kernel<<<pt.num_passes, RADIX, 0, st>>>(hist, base, pl.num_chunks);
+    RS_CUDA(cudaGetLastError(), RS_CALCULATION_FAILED);
+    s->launches++;
+    if (profile) RS_CUDA(cudaEventRecord(q.e[2], st), RS_CALCULATION_FAILED);
+
+    KeyT*     kb[2] = {buf0, buf1};
+    uint32_t* vb[2] = {vbuf0, vbuf1};
+    for (int p = 0; p < pt.num_passes; ++p) {
+        OnesweepArgs<KeyT> a{};
+        a.keys_in         = (p == 0) ? in : kb[(p - 1) & 1];
+        a.keys_out        = kb[p & 1];
+        a.vals_in         = has_vals ? ((p == 0) ? vin : vb[(p - 1) & 1]) : nullptr;
+        a.vals_out        = has_vals ? vb[p & 1] : nullptr;
+        a.n               = n;
+        a.base            = base + static_cast<size_t>(p) * pl.num_chunks * RADIX;
+        a.status          = status + static_cast<size_t>(p) * pl.num_tiles * RADIX;
+        a.counter         = ctr + p;
+        a.num_tiles       = static_cast<uint32_t>(pl.num_tiles);
+        a.tiles_per_chunk = pl.tiles_per_chunk;
+        a.digit           = pt.d[p];
+        a.use_tma = ((s->flags & RS_NO_TMA) == 0) && ((reinterpret_cast<uintptr_t>(a.keys_in) & 15u) == 0);
+        cudaError_t e = has_vals ? launch_pass<KeyT, true>(s->ctx, st, a) : launch_pass<KeyT, false>(s->ctx, st, a);
+        if (e != cudaSuccess) return fail(RS_CALCULATION_FAILED, "onesweep launch", e);
+        s->launches++;
+    }
+    if (profile) {
+        RS_CUDA(cudaEventRecord(q.e[3], st), RS_CALCULATION_FAILED);
+        s->pending.push_back(q);
+    }
+    s->last_passes      = pt.num_passes;
+    s->last_chunks      = pl.num_chunks;
+    s->last_hist_offset = pl.off_hist;
+    if (result_index) *result_index = (pt.num_passes - 1) & 1;
+    return RS_OK;
+}
+
+static int resolve_pending(rs_sorter s, bool block) {
+    size_t kept = 0;
+    for (size_t i = 0; i < s->pending.size(); ++i) {
+        EventQuad q = s->pending[i];
+        cudaError_t e = block ? cudaEventSynchronize(q.e[3]) : cudaEventQuery(q.e[3]);
+        if (e == cudaErrorNotReady) {
+            s->pending[kept++] = q;
+            continue;
+        }
+        if (e != cudaSuccess) return fail(RS_CALCULATION_FAILED, "event wait", e);
+        float h = 0, sc = 0, re = 0, to = 0;
+        cudaEventElapsedTime(&h, q.e[0], q.e[1]);
+        cudaEventElapsedTime(&sc, q.e[1], q.e[2]);
+        cudaEventElapsedTime(&re, q.e[2], q.e[3]);
+        cudaEventElapsedTime(&to, q.e[0], q.e[3]);
+        stat_update(s->rt.time_histo, h);
+        stat_update(s->rt.time_scan, sc);
+        stat_update(s->rt.time_reorder, re);
+        stat_update(s->rt.time_paste, 0.0);
+        stat_update(s->rt.time_total, to);
+        s->free_events.push_back(q);
+    }
+    s->pending.resize(kept);
+    return RS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// utility kernels (dataset fill, checks, lower bound, iota, pad)
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ static inline uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ static inline uint64_t counter_rand(uint64_t seed, uint64_t i) {
+    return mix64(seed + (i + 1) * 0x9E3779B97F4A7C15ull);
+}
+
+template <typename U>
+__global__ void rs_fill_kernel(U* out, uint64_t n, int kind, bool is_signed, uint64_t seed, uint64_t off, uint64_t total) {
+    const U sign = is_signed ? static_cast<U>(static_cast<U>(1) << (sizeof(U) * 8 - 1)) : static_cast<U>(0);
+    const U tmin = sign;                                  // bit pattern of numeric_limits<T>::min()
+    const U tmax = static_cast<U>(~static_cast<U>(0)) ^ sign;  // bit pattern of numeric_limits<T>::max()
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t g = off + i;
+        U v = 0;
+        switch (kind) {
+            case RS_DATASET_ZEROS: v = 0; break;
+            case RS_DATASET_RANGE: v = static_cast<U>(tmin + static_cast<U>(g)); break;
+            case RS_DATASET_INVERTED_RANGE: v = static_cast<U>(tmin + static_cast<U>(total - 1 - g)); break;
+            case RS_DATASET_UNIFORM:
+                v = static_cast<U>(counter_rand(seed, g));
+                if (g == 0) v = tmax;
+                if (g == total - 1) v = tmin;
+                break;
+            case RS_DATASET_RANDOM: v = static_cast<U>(static_cast<uint32_t>(counter_rand(seed ^ 0x52616e646f6dull, g))); break;
+        }
+        out[i] = v;
+    }
+}
+
+__global__ void rs_iota_kernel(uint32_t* out, uint64_t n) {
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+        out[i] = static_cast<uint32_t>(i);
+}
+
+template <typename U>
+__global__ void rs_fill_value_kernel(U* out, uint64_t first, uint64_t last, U v) {
+    for (uint64_t i = first + blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < last;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+        out[i] = v;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_xor(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v ^= __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename U>
+__global__ void rs_check_kernel(const U* keys, uint64_t n, U sign, unsigned long long* result) {
+    unsigned long long bad = 0, sum = 0, hsum = 0, hxor = 0;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const U k = keys[i];
+        if (i + 1 < n) {
+            const U nx = keys[i + 1];
+            if (static_cast<U>(nx ^ sign) < static_cast<U>(k ^ sign)) bad++;
+        }
+        const unsigned long long h = mix64(static_cast<uint64_t>(k) + 0x9E3779B97F4A7C15ull);
+        sum += static_cast<uint64_t>(k);
+        hsum += h;
+        hxor ^= h;
+    }
+    bad = warp_sum(bad); sum = warp_sum(sum); hsum = warp_sum(hsum); hxor = warp_xor(hxor);
+    if ((threadIdx.x & 31) == 0) {
+        if (bad) atomicAdd(&result[0], bad);
+        atomicAdd(&result[1], sum);
+        atomicAdd(&result[2], hsum);
+        atomicXor(&result[3], hxor);
+    }
+}
+
+template <typename U>
+__global__ void rs_check_perm_kernel(const U* kin, const U* kout, const uint32_t* perm, uint64_t n,
+                                     unsigned long long* result) {
+    unsigned long long mism = 0, unstable = 0;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t p = perm[i];
+        if (p >= n || kin[p] != kout[i]) mism++;
+        if (i + 1 < n && kout[i] == kout[i + 1] && p >= perm[i + 1]) unstable++;
+    }
+    mism = warp_sum(mism); unstable = warp_sum(unstable);
+    if ((threadIdx.x & 31) == 0) {
+        if (mism) atomicAdd(&result[0], mism);
+        if (unstable) atomicAdd(&result[1], unstable);
+    }
+}
+
+template <typename U>
+__global__ void rs_lower_bound_kernel(const U* keys, uint64_t n, const U* q, uint64_t nq, U sign, unsigned long long* out) {
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < nq;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const U x = static_cast<U>(q[i] ^ sign);
+        uint64_t lo = 0, hi = n;
+        while (lo < hi) {
+            const uint64_t mid = lo + ((hi - lo) >> 1);
+            if (static_cast<U>(keys[mid] ^ sign) < x) lo = mid + 1; else hi = mid;
+        }
+        out[i] = lo;
+    }
+}
+
+static int grid_for(uint64_t n, int threads, int sm_count) {
+    uint64_t g = (n + threads - 1) / threads;
+    return static_cast<int>(std::max<uint64_t>(1, std::min<uint64_t>(g, static_cast<uint64_t>(sm_count) * 16)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int rs_version(void) { return RSB200_VERSION_MAJOR * 1000 + RSB200_VERSION_MINOR; }
+
+const char* rs_status_string(int status) {
+    static const char* names[] = {"OK", "HOST_BUFFERS_FAILED", "INITIALIZATION_FAILED", "DATA_UPLOAD_FAILED",
+                                  "CALCULATION_FAILED", "DATA_DOWNLOAD_FAILED", "CLEANUP_FAILED", "RESIZE_FAILED",
+                                  "KERNEL_CREATION_FAILED", "PROGRAM_CREATION_FAILED", "NO_SOURCE_FOUND",
+                                  "LOADING_SOURCE_FAILED"};
+    if (status < 0 || status > 11) return "UNKNOWN";
+    return names[status];
+}
+
+const char* rs_last_error_string(void) { return g_last_error.c_str(); }
+
+int rs_device_count(int* n) {
+    if (!n) return fail(RS_INITIALIZATION_FAILED, "null argument");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        *n = 0;
+        return fail(RS_INITIALIZATION_FAILED, "cudaGetDeviceCount", e);
+    }
+    *n = c;
+    return RS_OK;
+}
+
+int rs_context_create(int device, rs_context* out) {
+    if (!out) return fail(RS_INITIALIZATION_FAILED, "null argument");
+    *out = nullptr;
+    int count = 0;
+    RS_CUDA(cudaGetDeviceCount(&count), RS_INITIALIZATION_FAILED);
+    if (device < 0 || device >= count) return fail(RS_INITIALIZATION_FAILED, "no such CUDA device");
+    RS_CUDA(cudaSetDevice(device), RS_INITIALIZATION_FAILED);
+    int major = 0, sms = 0, smem = 0;
+    RS_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device), RS_INITIALIZATION_FAILED);
+    RS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device), RS_INITIALIZATION_FAILED);
+    RS_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device), RS_INITIALIZATION_FAILED);
+    if (major != 10) return fail(RS_INITIALIZATION_FAILED, "librsb200 is built for sm_100a (B200) only");
+    rs_context c = new (std::nothrow) rs_context_s{device, sms, smem};
+    if (!c) return fail(RS_INITIALIZATION_FAILED, "out of host memory");
+    *out = c;
+    return RS_OK;
+}
+
+int rs_context_destroy(rs_context ctx) {
+    delete ctx;
+    return RS_OK;
+}
+
+int rs_context_sm_count(rs_context ctx, int* n) {
+    if (!ctx || !n) return fail(RS_INITIALIZATION_FAILED, "null argument");
+    *n = ctx->sm_count;
+    return RS_OK;
+}
+
+int rs_stream_create(rs_context ctx, rs_stream* out) {
+    if (!ctx || !out) return fail(RS_INITIALIZATION_FAILED, "null argument");
+    RS_CUDA(cudaSetDevice(ctx->device), RS_INITIALIZATION_FAILED);
+    cudaStream_t st;
+    RS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), RS_INITIALIZATION_FAILED);
+    *out = new rs_stream_s{ctx, st, true};
+    return RS_OK;
+}
+
+int rs_stream_wrap(rs_context ctx, void* cuda_stream, rs_stream* out) {
+    if (!ctx || !out) return fail(RS_INITIALIZATION_FAILED, "null argument");
+    *out = new rs_stream_s{ctx, static_cast<cudaStream_t>(cuda_stream), false};
+    return RS_OK;
+}
+
+int rs_stream_sync(rs_stream s) {
+    if (!s) return fail(RS_CALCULATION_FAILED, "null stream");
+    RS_CUDA(cudaSetDevice(s->ctx->device), RS_CALCULATION_FAILED);
+    RS_CUDA(cudaStreamSynchronize(s->st), RS_CALCULATION_FAILED);
+    return RS_OK;
+}
+
+int rs_stream_destroy(rs_stream s) {
+    if (!s) return RS_OK;
+    if (s->owned) {
+        cudaSetDevice(s->ctx->device);
+        cudaStreamDestroy(s->st);
+    }
+    delete s;
+    return RS_OK;
+}
+
+int rs_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(RS_HOST_BUFFERS_FAILED, "null argument");
+    *out = nullptr;
+    RS_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault), RS_HOST_BUFFERS_FAILED);
+    return RS_OK;
+}
+int rs_host_free(void* p) {
+    if (p) RS_CUDA(cudaFreeHost(p), RS_CLEANUP_FAILED);
+    return RS_OK;
+}
+
+uint64_t rs_round_up_keys(uint64_t n) {
+    const uint64_t items = 1024;  // _NUM_GROUPS * _NUM_ITEMS_PER_GROUP of the reference
+    const uint64_t rest  = n % items;
+    return rest ? n + (items - rest) : n;
+}
+
+int rs_sorter_create(rs_context ctx, rs_key_type type, uint64_t max_keys, uint32_t flags, rs_sorter* out) {
+    if (!ctx || !out) return fail(RS_INITIALIZATION_FAILED, "null argument");
+    *out = nullptr;
+    if (type < RS_KEY_U32 || type > RS_KEY_I64) return fail(RS_INITIALIZATION_FAILED, "unknown key type");
+    RS_CUDA(cudaSetDevice(ctx->device), RS_INITIALIZATION_FAILED);
+    rs_sorter s = new (std::nothrow) rs_sorter_s{};
+    if (!s) return fail(RS_INITIALIZATION_FAILED, "out of host memory");
+    s->ctx       = ctx;
+    s->type      = type;
+    s->flags     = flags;
+    s->max_keys  = max_keys;
+    s->key_bytes = (type == RS_KEY_U32 || type == RS_KEY_I32) ? 4 : 8;
+    s->is_signed = (type == RS_KEY_I32 || type == RS_KEY_I64);
+    s->has_vals  = (flags & RS_WITH_PERMUTATION) != 0;
+    stat_reset(s->rt.time_histo); stat_reset(s->rt.time_scan); stat_reset(s->rt.time_reorder);
+    stat_reset(s->rt.time_paste); stat_reset(s->rt.time_total);
+    if (s->has_vals && max_keys > (1ull << 32)) {
+        delete s;
+        return fail(RS_INITIALIZATION_FAILED, "a uint32 permutation cannot index more than 2^32 keys");
+    }
+    const uint64_t alloc_keys = std::max<uint64_t>(max_keys, 1);
+    // scratch sized for the worst plan: the keys-only tile may differ from the key+value tile
+    const int full_passes = static_cast<int>(s->key_bytes);
+    size_t need = std::max(make_plan(alloc_keys, s->key_bytes, false, full_passes).total,
+                           make_plan(alloc_keys, s->key_bytes, true, full_passes).total);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&s->scratch), need);
+    if (e != cudaSuccess) { delete s; return fail(RS_INITIALIZATION_FAILED, "cudaMalloc scratch", e); }
+    s->scratch_bytes = need;
+    if (!(flags & RS_NO_KEY_BUFFERS)) {
+        for (int i = 0; i < 2; ++i) {
+            e = cudaMalloc(&s->keys[i], alloc_keys * s->key_bytes);
+            if (e == cudaSuccess && s->has_vals) e = cudaMalloc(reinterpret_cast<void**>(&s->vals[i]), alloc_keys * sizeof(uint32_t));
+            if (e != cudaSuccess) {
+                rs_sorter_destroy(s);
+                return fail(RS_INITIALIZATION_FAILED, "cudaMalloc key/permutation buffers", e);
+            }
+        }
+    }
+    *out = s;
+    return RS_OK;
+}
+
+int rs_sorter_destroy(rs_sorter s) {
+    if (!s) return RS_OK;
+    cudaSetDevice(s->ctx->device);
+    int rc = RS_OK;
+    for (auto& q : s->pending) for (auto& e : q.e) cudaEventDestroy(e);
+    for (auto& q : s->free_events) for (auto& e : q.e) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (s->keys[i] && cudaFree(s->keys[i]) != cudaSuccess) rc = RS_CLEANUP_FAILED;
+        if (s->vals[i] && cudaFree(s->vals[i]) != cudaSuccess) rc = RS_CLEANUP_FAILED;
+    }
+    if (s->scratch && cudaFree(s->scratch) != cudaSuccess) rc = RS_CLEANUP_FAILED;
+    delete s;
+    return rc;
+}
+
+int rs_sorter_pad(rs_sorter s, rs_stream st, uint64_t first_key, uint64_t rounded) {
+    if (!s || !st) return fail(RS_CALCULATION_FAILED, "null argument");
+    if (!s->keys[0]) return fail(RS_CALCULATION_FAILED, "sorter has no key buffers");
+    if (rounded > s->max_keys || first_key > rounded) return fail(RS_RESIZE_FAILED, "pad range exceeds max_keys");
+    if (first_key == rounded) return RS_OK;
+    RS_CUDA(cudaSetDevice(s->ctx->device), RS_CALCULATION_FAILED);
+    const int g = grid_for(rounded - first_key, 256, s->ctx->sm_count);
+    // pattern = numeric_limits<T>::max() - 1 (src/RadixSortGPU.cpp:274-276)
+    if (s->key_bytes == 4) {
+        const uint32_t v = (s->is_signed ? 0x7fffffffu : 0xffffffffu) - 1u;
+        rs_fill_value_kernel<uint32_t><<<g, 256, 0, st->st>>>(static_cast<uint32_t*>(s->keys[0]), first_key, rounded, v);
+    } else {
+        const uint64_t v = (s->is_signed ? 0x7fffffffffffffffull : 0xffffffffffffffffull) - 1ull;
+        rs_fill_value_kernel<uint64_t><<<g, 256, 0, st->st>>>(static_cast<uint64_t*>(s->keys[0]), first_key, rounded, v);
+    }
+    RS_CUDA(cudaGetLastError(), RS_CALCULATION_FAILED);
+    s->launches++;
+    return RS_OK;
+}
+
+int rs_sorter_upload(rs_sorter s, rs_stream st, const void* h_keys, const uint32_t* h_perm, uint64_t n) {
+    if (!s || !st) return fail(RS_DATA_UPLOAD_FAILED, "null argument");
+    if (!s->keys[0]) return fail(RS_DATA_UPLOAD_FAILED, "sorter has no key buffers");
+    if (n > s->max_keys) return fail(RS_DATA_UPLOAD_FAILED, "n exceeds max_keys");
+    if (n && !h_keys) return fail(RS_HOST_BUFFERS_FAILED, "null host key buffer");
+    RS_CUDA(cudaSetDevice(s->ctx->device), RS_DATA_UPLOAD_FAILED);
+    if (n == 0) return RS_OK;
+    RS_CUDA(cudaMemcpyAsync(s->keys[0], h_keys, n * s->key_bytes, cudaMemcpyHostToDevice, st->st), RS_DATA_UPLOAD_FAILED);
+    if (s->has_vals) {
+        if (h_perm) {
+            RS_CUDA(cudaMemcpyAsync(s->vals[0], h_perm, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st->st),
+                    RS_DATA_UPLOAD_FAILED);
+        } else {
+            rs_iota_kernel<<<grid_for(n, 256, s->ctx->sm_count), 256, 0, st->st>>>(s->vals[0], n);
+            RS_CUDA(cudaGetLastError(), RS_DATA_UPLOAD_FAILED);
+            s->launches++;
+        }
+    }
+    return RS_OK;
+}
+
+int rs_sorter_sort_device(rs_sorter s, rs_stream st, const void* d_keys_in, void* d_keys_buf0, void* d_keys_buf1,
+                          const uint32_t* d_vals_in, uint32_t* d_vals_buf0, uint32_t* d_vals_buf1, uint64_t n,
+                          int begin_bit, int end_bit, int* result_index) {
+    if (!s || !st) return fail(RS_CALCULATION_FAILED, "null argument");
+    const int key_bits = static_cast<int>(s->key_bytes) * 8;
+    if (begin_bit < 0 || end_bit > key_bits || begin_bit >= end_bit) return fail(RS_CALCULATION_FAILED, "bad bit range");
+    const int passes = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
+    if (result_index) *result_index = (passes - 1) & 1;
+    if (!d_keys_in || !d_keys_buf0 || (passes > 1 && !d_keys_buf1)) return fail(RS_CALCULATION_FAILED, "null key buffer");
+    const bool has_vals = d_vals_in != nullptr;
+    if (has_vals && (!d_vals_buf0 || (passes > 1 && !d_vals_buf1))) return fail(RS_CALCULATION_FAILED, "null value buffer");
+    if (has_vals && n > (1ull << 32)) return fail(RS_CALCULATION_FAILED, "uint32 payload limited to 2^32 keys");
+    RS_CUDA(cudaSetDevice(s->ctx->device), RS_CALCULATION_FAILED);
+    const bool profile = (s->flags & RS_NO_PROFILE) == 0;
+    if (profile) {
+        int rc = resolve_pending(s, false);
+        if (rc != RS_OK) return rc;
+    }
+    if (n == 0) return RS_OK;
+    if (s->key_bytes == 4)
+        return sort_typed<uint32_t>(s, st->st, static_cast<const uint32_t*>(d_keys_in), static_cast<uint32_t*>(d_keys_buf0),
+                                    static_cast<uint32_t*>(d_keys_buf1), d_vals_in, d_vals_buf0, d_vals_buf1, n, begin_bit,
+                                    end_bit, profile, result_index);
+    return sort_typed<uint64_t>(s, st->st, static_cast<const uint64_t*>(d_keys_in), static_cast<uint64_t*>(d_keys_buf0),
+                                static_cast<uint64_t*>(d_keys_buf1), d_vals_in, d_vals_buf0, d_vals_buf1, n, begin_bit,
+                                end_bit, profile, result_index);
+}
+
+int rs_sorter_sort(rs_sorter s, rs_stream st, uint64_t n) {
+    if (!s || !st) return fail(RS_CALCULATION_FAILED, "null argument");
+    if (!s->keys[0]) return fail(RS_CALCULATION_FAILED, "sorter has no key buffers");
+    if (n > s->max_keys) return fail(RS_CALCULATION_FAILED, "n exceeds max_keys");
+    s->last_n = n;
+    // pass p: keys[p&1] -> keys[(p+1)&1]; uploaded data lives in keys[0]
+    int idx = 0;
+    int rc  = rs_sorter_sort_device(s, st, s->keys[0], s->keys[1], s->keys[0], s->has_vals ? s->vals[0] : nullptr,
+                                    s->has_vals ? s->vals[1] : nullptr, s->has_vals ? s->vals[0] : nullptr, n, 0,
+                                    static_cast<int>(s->key_bytes) * 8, &idx);
+    if (rc != RS_OK) return rc;
+    s->result_index = (idx == 0) ? 1 : 0;  // buf0 is keys[1], buf1 is keys[0]
+    if (n == 0) s->result_index = 0;
+    return RS_OK;
+}
+
+int rs_sorter_download(rs_sorter s, rs_stream st, void* h_keys_out, uint32_t* h_perm_out, uint64_t n) {
+    if (!s || !st) return fail(RS_DATA_DOWNLOAD_FAILED, "null argument");
+    if (!s->keys[0]) return fail(RS_DATA_DOWNLOAD_FAILED, "sorter has no key buffers");
+    if (n > s->max_keys) return fail(RS_DATA_DOWNLOAD_FAILED, "n exceeds max_keys");
+    RS_CUDA(cudaSetDevice(s->ctx->device), RS_DATA_DOWNLOAD_FAILED);
+    const int r = s->result_index;
+    if (n && h_keys_out)
+        RS_CUDA(cudaMemcpyAsync(h_keys_out, s->keys[r], n * s->key_bytes, cudaMemcpyDeviceToHost, st->st),
+                RS_DATA_DOWNLOAD_FAILED);
+    if (n && h_perm_out) {
+        if (!s->has_vals) return fail(RS_DATA_DOWNLOAD_FAILED, "sorter was created without RS_WITH_PERMUTATION");
+        RS_CUDA(cudaMemcpyAsync(h_perm_out, s->vals[r], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st->st),
+                RS_DATA_DOWNLOAD_FAILED);
+    }
+    RS_CUDA(cudaStreamSynchronize(st->st), RS_DATA_DOWNLOAD_FAILED);
+    return RS_OK;
+}
+
+int rs_sorter_download_histograms(rs_sorter s, rs_stream st, uint64_t* h_hist, size_t capacity, int* passes) {
+    if (!s || !st || !h_hist) return fail(RS_DATA_DOWNLOAD_FAILED, "null argument");
+    RS_CUDA(cudaSetDevice(s->ctx->device), RS_DATA_DOWNLOAD_FAILED);
+    const int P = s->last_passes, C = s->last_chunks;
+    if (passes) *passes = P;
+    if (P == 0) return RS_OK;
+    if (capacity < static_cast<size_t>(P) * RADIX) return fail(RS_HOST_BUFFERS_FAILED, "histogram buffer too small");
+    std::vector<uint64_t> tmp(static_cast<size_t>(P) * C * RADIX);
+    RS_CUDA(cudaMemcpyAsync(tmp.data(), s->scratch + s->last_hist_offset, tmp.size() * sizeof(uint64_t),
+                            cudaMemcpyDeviceToHost, st->st), RS_DATA_DOWNLOAD_FAILED);
+    RS_CUDA(cudaStreamSynchronize(st->st), RS_DATA_DOWNLOAD_FAILED);
+    for (int p = 0; p < P; ++p)
+        for (int d = 0; d < RADIX; ++d) {
+            uint64_t sum = 0;
+            for (int c = 0; c < C; ++c) sum += tmp[(static_cast<size_t>(p) * C + c) * RADIX + d];
+            h_hist[static_cast<size_t>(p) * RADIX + d] = sum;
+        }
+    return RS_OK;
+}
+
+int rs_sorter_runtimes(rs_sorter s, rs_runtimes* out) {
+    if (!s || !out) return fail(RS_CALCULATION_FAILED, "null argument");
+    RS_CUDA(cudaSetDevice(s->ctx->device), RS_CALCULATION_FAILED);
+    int rc = resolve_pending(s, true);
+    if (rc != RS_OK) return rc;
+    *out = s->rt;
+    return RS_OK;
+}
+
+int rs_sorter_reset_runtimes(rs_sorter s) {
+    if (!s) return fail(RS_CALCULATION_FAILED, "null argument");
+    cudaSetDevice(s->ctx->device);
+    resolve_pending(s, true);
+    stat_reset(s->rt.time_histo); stat_reset(s->rt.time_scan); stat_reset(s->rt.time_reorder);
+    stat_reset(s->rt.time_paste); stat_reset(s->rt.time_total);
+    return RS_OK;
+}
+
+int rs_sorter_launch_count(rs_sorter s, uint64_t* out) {
+    if (!s || !out) return fail(RS_CALCULATION_FAILED, "null argument");
+    *out = s->launches;
+    return RS_OK;
+}
+
+int rs_dataset_fill_device(rs_context ctx, rs_stream st, rs_key_type type, rs_dataset_kind kind, uint64_t seed,
+                           uint64_t global_offset, uint64_t total_n, void* d_out, uint64_t n) {
+    if (!ctx || !st || (!d_out && n)) return fail(RS_CALCULATION_FAILED, "null argument");
+    if (kind < RS_DATASET_ZEROS || kind > RS_DATASET_RANDOM) return fail(RS_CALCULATION_FAILED, "unknown dataset kind");
+    if (n == 0) return RS_OK;
+    RS_CUDA(cudaSetDevice(ctx->device), RS_CALCULATION_FAILED);
+    const bool sg = (type == RS_KEY_I32 || type == RS_KEY_I64);
+    const int  g  = grid_for(n, 256, ctx->sm_count);
+    if (type == RS_KEY_U32 || type == RS_KEY_I32)
+        rs_fill_kernel<uint32_t><<<g, 256, 0, st->st>>>(static_cast<uint32_t*>(d_out), n, kind, sg, seed, global_offset, total_n);
+    else
+        rs_fill_kernel<uint64_t><<<g, 256, 0, st->st>>>(static_cast<uint64_t*>(d_out), n, kind, sg, seed, global_offset, total_n);
+    RS_CUDA(cudaGetLastError(), RS_CALCULATION_FAILED);
+    return RS_OK;
+}
+
+int rs_check_device(rs_context ctx, rs_stream st, rs_key_type type, const void* d_keys, uint64_t n, uint64_t result[4]) {
+    if (!ctx || !st || !result || (!d_keys && n)) return fail(RS_CALCULATION_FAILED, "null argument");
+    RS_CUDA(cudaSetDevice(ctx->device), RS_CALCULATION_FAILED);
+    unsigned long long* d_res = nullptr;
+    RS_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_res), 4 * sizeof(unsigned long long)), RS_CALCULATION_FAILED);
+    cudaMemsetAsync(d_res, 0, 4 * sizeof(unsigned long long), st->st);
+    if (n) {
+        const bool sg = (type == RS_KEY_I32 || type == RS_KEY_I64);
+        const int  g  = grid_for(n, 256, ctx->sm_count);
+        if (type == RS_KEY_U32 || type == RS_KEY_I32)
+            rs_check_kernel<uint32_t><<<g, 256, 0, st->st>>>(static_cast<const uint32_t*>(d_keys), n, sg ? 0x80000000u : 0u, d_res);
+        else
+            rs_check_kernel<uint64_t><<<g, 256, 0, st->st>>>(static_cast<const uint64_t*>(d_keys), n,
+                                                            sg ? 0x8000000000000000ull : 0ull, d_res);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(result, d_res, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st->st);
+    cudaFree(d_res);
+    if (e != cudaSuccess) return fail(RS_CALCULATION_FAILED, "rs_check_device", e);
+    return RS_OK;
+}
+
+int rs_check_permutation_device(rs_context ctx, rs_stream st, rs_key_type type, const void* d_keys_in,
+                                const void* d_keys_out, const uint32_t* d_perm, uint64_t n, uint64_t result[2]) {
+    if (!ctx || !st || !result) return fail(RS_CALCULATION_FAILED, "null argument");
+    RS_CUDA(cudaSetDevice(ctx->device), RS_CALCULATION_FAILED);
+    unsigned long long* d_res = nullptr;
+    RS_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_res), 2 * sizeof(unsigned long long)), RS_CALCULATION_FAILED);
+    cudaMemsetAsync(d_res, 0, 2 * sizeof(unsigned long long), st->st);
+    if (n) {
+        const int g = grid_for(n, 256, ctx->sm_count);
+        if (type == RS_KEY_U32 || type == RS_KEY_I32)
+            rs_check_perm_kernel<uint32_t><<<g, 256, 0, st->st>>>(static_cast<const uint32_t*>(d_keys_in),
+                                                                 static_cast<const uint32_t*>(d_keys_out), d_perm, n, d_res);
+        else
+            rs_check_perm_kernel<uint64_t><<<g, 256, 0, st->st>>>(static_cast<const uint64_t*>(d_keys_in),
+                                                                 static_cast<const uint64_t*>(d_keys_out), d_perm, n, d_res);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(result, d_res, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st->st);
+    cudaFree(d_res);
+    if (e != cudaSuccess) return fail(RS_CALCULATION_FAILED, "rs_check_permutation_device", e);
+    return RS_OK;
+}
+
+int rs_lower_bound_device(rs_context ctx, rs_stream st, rs_key_type type, const void* d_keys, uint64_t n,
+                          const void* d_queries, uint64_t num_queries, uint64_t* d_out) {
+    if (!ctx || !st || (num_queries && (!d_queries || !d_out))) return fail(RS_CALCULATION_FAILED, "null argument");
+    if (num_queries == 0) return RS_OK;
+    RS_CUDA(cudaSetDevice(ctx->device), RS_CALCULATION_FAILED);
+    const bool sg = (type == RS_KEY_I32 || type == RS_KEY_I64);
+    const int  g  = grid_for(num_queries, 128, ctx->sm_count);
+    auto* out = reinterpret_cast<unsigned long long*>(d_out);
+    if (type == RS_KEY_U32 || type == RS_KEY_I32)
+        rs_lower_bound_kernel<uint32_t><<<g, 128, 0, st->st>>>(static_cast<const uint32_t*>(d_keys), n,
+                                                              static_cast<const uint32_t*>(d_queries), num_queries,
+                                                              sg ? 0x80000000u : 0u, out);
+    else
+        rs_lower_bound_kernel<uint64_t><<<g, 128, 0, st->st>>>(static_cast<const uint64_t*>(d_keys), n,
+                                                              static_cast<const uint64_t*>(d_queries), num_queries,
+                                                              sg ? 0x8000000000000000ull : 0ull, out);
+    RS_CUDA(cudaGetLastError(), RS_CALCULATION_FAILED);
+    return RS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,476 @@
+// rs_kernels.cuh -- sm_100a device code of the B200-native LSD radix sort.
+//
+// Replaces the four OpenCL kernels of the reference (src/kernels/RadixSort.cl:16-197):
+//   histogram        (:16-71)   -> rs_histogram_kernel : ONE read of all keys builds the 256-bin
+//                                  histograms of every 8-bit digit (all passes) at once
+//   scanhistograms x2 (:125-181)
+//   pastehistograms  (:185-197) -> rs_scan_kernel (tiny) + decoupled look-back inside the pass kernel
+//   reorder          (:74-119)  -> rs_onesweep_kernel : one stable scatter pass per digit; a tile's
+//                                  global offsets come from a chained scan over per-tile status words
+// The key transform `key + OFFSET` (:51,109,114 with OFFSET from src/RadixSortGPU.cpp:436) is a
+// sign-bit flip; it is folded into the digit extraction of the pass that holds the sign bit.
+//
+// Data layout in HBM (all owned by rs_sorter, see rs_api.cu):
+//   keys   : T[n] ping-pong pair           values : uint32[n] ping-pong pair (optional)
+//   hist   : uint64[passes][chunks][256]   digit counts per lookback chunk
+//   base   : uint64[passes][chunks][256]   global output offset of (chunk, digit)
+//   status : uint32[passes][tiles][256]    2 flag bits | 30-bit count  (look-back words)
+//   ctr    : uint32[passes]                dynamic tile-id dispensers
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace rsb {
+
+constexpr int      RADIX_BITS        = 8;
+constexpr int      RADIX             = 1 << RADIX_BITS;
+constexpr uint32_t STATUS_LOCAL      = 1u << 30;   // tile aggregate available
+constexpr uint32_t STATUS_INCLUSIVE  = 2u << 30;   // inclusive prefix (within chunk) available
+constexpr uint32_t STATUS_VALUE_MASK = (1u << 30) - 1u;
+constexpr uint64_t CHUNK_MAX_KEYS    = (1ull << 30) - 1ull;  // a look-back chain never sums past this
+constexpr int      MAX_PASSES        = 8;
+
+struct DigitSpec {
+    int      shift;  // first bit of the digit
+    uint32_t mask;   // (1<<bits)-1
+    uint32_t flip;   // xor applied to the digit (sign bit of signed keys), else 0
+};
+
+struct PassTable {
+    int       num_passes;
+    DigitSpec d[MAX_PASSES];
+};
+
+template <typename KeyT>
+__device__ __forceinline__ uint32_t digit_of(KeyT k, const DigitSpec& s) {
+    return (static_cast<uint32_t>(k >> s.shift) & s.mask) ^ s.flip;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small PTX helpers (mbarrier + bulk async copy = the TMA 1-D path, SASS: UBLKCP / SYNCS)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void bulk_load_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t ld_status(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Upfront multi-digit histogram.  One coalesced 128-bit read of every key; all `num_passes`
+// digit histograms are accumulated in shared memory and flushed once per (block, chunk).
+// A warp-uniform shortcut keeps degenerate inputs (Zeros, Range, Inverted Range: whole 128-key
+// rows share a digit) from serialising on one shared-memory word: the bits that differ across
+// the row are OR-reduced (REDUX) and a digit whose bits do not differ is counted by one lane.
+// Algorithmic traffic: sizeof(KeyT) bytes read per key.
+// ------------------------------------------------------------------------------------------------
+constexpr int HIST_THREADS = 512;
+constexpr int HIST_VECS    = 4;  // 16-byte vectors in flight per thread
+
+template <typename KeyT, int NPASS>
+__device__ __forceinline__ void hist_accumulate_row(uint32_t* sh, const KeyT (&k)[16 / sizeof(KeyT)], bool active,
+                                                    const PassTable& pt, int lane) {
+    constexpr int KV = 16 / sizeof(KeyT);
+    // bits that differ from lane 0's first key anywhere in this warp row
+    KeyT ref  = k[0];
+    KeyT diff = 0;
+    if constexpr (sizeof(KeyT) == 4) {
+        ref = static_cast<KeyT>(__shfl_sync(0xffffffffu, static_cast<uint32_t>(k[0]), 0));
+    } else {
+        ref = static_cast<KeyT>(__shfl_sync(0xffffffffu, static_cast<unsigned long long>(k[0]), 0));
+    }
+#pragma unroll
+    for (int j = 0; j < KV; ++j) diff |= (k[j] ^ ref);
+    uint32_t dlo = static_cast<uint32_t>(diff);
+    uint32_t dhi = sizeof(KeyT) == 8 ? static_cast<uint32_t>(static_cast<uint64_t>(diff) >> 32) : 0u;
+    const bool all_active = __all_sync(0xffffffffu, active);
+    dlo = __reduce_or_sync(0xffffffffu, dlo);
+    if (sizeof(KeyT) == 8) dhi = __reduce_or_sync(0xffffffffu, dhi);
+    const uint64_t wdiff = (static_cast<uint64_t>(dhi) << 32) | dlo;
+#pragma unroll
+    for (int p = 0; p < NPASS; ++p) {
+        const DigitSpec s = pt.d[p];
+        const bool uniform = all_active && (((wdiff >> s.shift) & s.mask) == 0);
+        if (uniform) {
+            if (lane == 0) atomicAdd(&sh[p * RADIX + digit_of(k[0], s)], 32u * KV);
+        } else if (active) {
+#pragma unroll
+            for (int j = 0; j < KV; ++j) atomicAdd(&sh[p * RADIX + digit_of(k[j], s)], 1u);
+        }
+    }
+}
+
+template <typename KeyT, int NPASS>
+__global__ void __launch_bounds__(HIST_THREADS)
+rs_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, uint64_t chunk_keys, int num_chunks,
+                    unsigned long long* __restrict__ hist /* [NPASS][num_chunks][256] */, PassTable pt) {
+    constexpr int KV = 16 / sizeof(KeyT);
+    __shared__ uint32_t sh[NPASS * RADIX];
+    const int  tid     = threadIdx.x;
+    const int  lane    = tid & 31;
+    const bool aligned = (reinterpret_cast<uintptr_t>(keys) & 15u) == 0;
+
+    for (int c = 0; c < num_chunks; ++c) {
+        for (int i = tid; i < NPASS * RADIX; i += HIST_THREADS) sh[i] = 0;
+        __syncthreads();
+        const uint64_t cbeg = static_cast<uint64_t>(c) * chunk_keys;
+        const uint64_t cend = (cbeg + chunk_keys < n) ? cbeg + chunk_keys : n;
+        const uint64_t cnt  = cend - cbeg;
+        const KeyT*    ck   = keys + cbeg;  // chunk_keys is a multiple of the tile size => keeps 16B alignment
+        const uint64_t nvec = aligned ? cnt / KV : 0;
+        const uint4*   cv   = reinterpret_cast<const uint4*>(ck);
+
+        // whole warps walk the vector range so the warp-uniform shortcut sees full rows
+        const uint64_t stride = static_cast<uint64_t>(gridDim.x) * HIST_THREADS;
+        const uint64_t first  = static_cast<uint64_t>(blockIdx.x) * HIST_THREADS + tid;
+        const uint64_t rounds = (nvec + stride * HIST_VECS - 1) / (stride * HIST_VECS);
+        for (uint64_t r = 0; r < rounds; ++r) {
+            uint4 v[HIST_VECS];
+            bool  act[HIST_VECS];
+#pragma unroll
+            for (int u = 0; u < HIST_VECS; ++u) {
+                const uint64_t idx = first + (r * HIST_VECS + u) * stride;
+                act[u]             = idx < nvec;
+                v[u]               = act[u] ? __ldg(cv + idx) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < HIST_VECS; ++u) {
+                KeyT k[KV];
+                if constexpr (sizeof(KeyT) == 4) {
+                    k[0]      = static_cast<KeyT>(v[u].x);
+                    k[1 % KV] = static_cast<KeyT>(v[u].y);
+                    k[2 % KV] = static_cast<KeyT>(v[u].z);
+                    k[3 % KV] = static_cast<KeyT>(v[u].w);
+                } else {
+                    k[0]      = static_cast<KeyT>((static_cast<uint64_t>(v[u].y) << 32) | v[u].x);
+                    k[1 % KV] = static_cast<KeyT>((static_cast<uint64_t>(v[u].w) << 32) | v[u].z);
+                }
+                hist_accumulate_row<KeyT, NPASS>(sh, k, act[u], pt, lane);
+            }
+        }
+        // scalar tail (and the whole chunk when the base pointer is not 16-byte aligned)
+        for (uint64_t i = nvec * KV + first; i < cnt; i += stride) {
+            const KeyT k = ck[i];
+#pragma unroll
+            for (int p = 0; p < NPASS; ++p) atomicAdd(&sh[p * RADIX + digit_of(k, pt.d[p])], 1u);
+        }
+        __syncthreads();
+        for (int i = tid; i < NPASS * RADIX; i += HIST_THREADS) {
+            const uint32_t v = sh[i];
+            if (v) {
+                const int p = i / RADIX, d = i % RADIX;
+                atomicAdd(&hist[(static_cast<size_t>(p) * num_chunks + c) * RADIX + d],
+                          static_cast<unsigned long long>(v));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Digit-offset scan: one block per pass.  base[p][c][d] = #keys with digit < d (all chunks)
+//                                                       + #keys with digit d in chunks < c.
+// Replaces scanhistograms x2 + pastehistograms of the reference for the GLOBAL part; the per-tile
+// part is the look-back inside rs_onesweep_kernel.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RADIX)
+rs_scan_kernel(const unsigned long long* __restrict__ hist, unsigned long long* __restrict__ base, int num_chunks) {
+    __shared__ unsigned long long wsum[RADIX / 32];
+    const int    p    = blockIdx.x;
+    const int    d    = threadIdx.x;
+    const int    lane = d & 31, warp = d >> 5;
+    const size_t row  = static_cast<size_t>(p) * num_chunks * RADIX;
+    unsigned long long total = 0;
+    for (int c = 0; c < num_chunks; ++c) total += hist[row + static_cast<size_t>(c) * RADIX + d];
+    unsigned long long incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    unsigned long long woff = 0;
+    for (int w = 0; w < warp; ++w) woff += wsum[w];
+    unsigned long long run = woff + incl - total;
+    for (int c = 0; c < num_chunks; ++c) {
+        base[row + static_cast<size_t>(c) * RADIX + d] = run;
+        run += hist[row + static_cast<size_t>(c) * RADIX + d];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Onesweep pass: persistent CTAs take tile ids from an atomic dispenser, prefetch the NEXT tile's
+// keys into shared memory with a 1-D bulk async copy (TMA) while ranking the current one, rank the
+// digits with __match_any_sync + per-warp counters, resolve the tile's global digit offsets with a
+// decoupled look-back over status words, stage the keys (and values) in shared memory in ranked
+// order and write them out in coalesced per-digit runs.  Stable.
+// Algorithmic traffic: sizeof(KeyT) read + sizeof(KeyT) written per key (+4+4 with values).
+// ------------------------------------------------------------------------------------------------
+template <typename KeyT>
+struct OnesweepArgs {
+    const KeyT*               keys_in;
+    KeyT*                     keys_out;
+    const uint32_t*           vals_in;
+    uint32_t*                 vals_out;
+    uint64_t                  n;
+    const unsigned long long* base;    // [chunks][256] for this pass
+    uint32_t*                 status;  // [tiles][256] for this pass, zeroed
+    uint32_t*                 counter; // tile-id dispenser for this pass, zeroed
+    uint32_t                  num_tiles;
+    uint32_t                  tiles_per_chunk;
+    DigitSpec                 digit;
+    int                       use_tma;
+};
+
+template <typename KeyT, bool HAS_VALS, int THREADS, int KPT>
+struct OnesweepSmem {
+    static constexpr int    TILE   = THREADS * KPT;
+    static constexpr int    NWARPS = THREADS / 32;
+    static constexpr size_t stage_bytes = sizeof(KeyT) * TILE;
+    static constexpr size_t off_stage0  = 0;
+    static constexpr size_t off_stage1  = off_stage0 + stage_bytes;
+    static constexpr size_t off_vstage  = off_stage1 + stage_bytes;
+    static constexpr size_t off_whist   = off_vstage + (HAS_VALS ? sizeof(uint32_t) * TILE : 0);
+    static constexpr size_t off_gbase   = off_whist + sizeof(uint32_t) * NWARPS * RADIX;
+    static constexpr size_t off_wsum    = off_gbase + sizeof(unsigned long long) * RADIX;
+    static constexpr size_t off_mbar    = off_wsum + sizeof(uint32_t) * 16;
+    static constexpr size_t off_tile    = off_mbar + sizeof(uint64_t) * 2;
+    static constexpr size_t total       = off_tile + sizeof(uint32_t) * 4;
+};
+
+template <typename KeyT, bool HAS_VALS, int THREADS, int KPT, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
+rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
+    using L = OnesweepSmem<KeyT, HAS_VALS, THREADS, KPT>;
+    constexpr int TILE   = L::TILE;
+    constexpr int NWARPS = L::NWARPS;
+    static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit needed");
+    static_assert((sizeof(KeyT) * TILE) % 128 == 0, "stage must keep 128B alignment");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    KeyT* const         stage0   = reinterpret_cast<KeyT*>(smem_raw + L::off_stage0);  // stage s = stage0 + s*TILE
+    uint32_t*           vstage   = reinterpret_cast<uint32_t*>(smem_raw + L::off_vstage);
+    uint32_t*           whist    = reinterpret_cast<uint32_t*>(smem_raw + L::off_whist);
+    unsigned long long* gbase    = reinterpret_cast<unsigned long long*>(smem_raw + L::off_gbase);
+    uint32_t*           wsum     = reinterpret_cast<uint32_t*>(smem_raw + L::off_wsum);
+    uint64_t*           mbar     = reinterpret_cast<uint64_t*>(smem_raw + L::off_mbar);
+    volatile uint32_t*  sh_tile  = reinterpret_cast<volatile uint32_t*>(smem_raw + L::off_tile);
+
+    const int       tid  = threadIdx.x;
+    const int       lane = tid & 31;
+    const int       warp = tid >> 5;
+    const uint32_t  lt   = lanemask_lt();
+    const DigitSpec ds   = a.digit;
+    const uint32_t  full_tiles = static_cast<uint32_t>(a.n / TILE);  // tiles [0, full_tiles) are complete
+    uint32_t* const mywh = whist + warp * RADIX;
+
+    auto issue_prefetch = [&](uint32_t t, int s) {
+        // thread 0 only: bulk copy of a complete tile into stage s
+        if (a.use_tma && t < full_tiles) {
+            fence_proxy_async_smem();  // earlier generic-proxy writes to this stage are ordered before the copy
+            mbar_expect_tx(&mbar[s], static_cast<uint32_t>(L::stage_bytes));
+            bulk_load_g2s(stage0 + s * TILE, a.keys_in + static_cast<uint64_t>(t) * TILE, static_cast<uint32_t>(L::stage_bytes),
+                          &mbar[s]);
+        }
+    };
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        mbar_fence_init();
+        const uint32_t t0 = atomicAdd(a.counter, 1u);
+        sh_tile[0]        = t0;
+        if (t0 < a.num_tiles) issue_prefetch(t0, 0);
+    }
+    __syncthreads();
+
+    uint32_t phase_bits = 0;  // bit s = parity to wait for on mbar[s]
+    int      s          = 0;
+    while (true) {
+        const uint32_t t = sh_tile[s];
+        if (t >= a.num_tiles) break;
+        if (tid == 0) {
+            const uint32_t tn = atomicAdd(a.counter, 1u);
+            sh_tile[s ^ 1]    = tn;
+            if (tn < a.num_tiles) issue_prefetch(tn, s ^ 1);
+        }
+        const bool     is_full = t < full_tiles;
+        const bool     via_tma = a.use_tma && is_full;
+        const uint64_t tile_base = static_cast<uint64_t>(t) * TILE;
+        const uint32_t valid   = is_full ? TILE : static_cast<uint32_t>(a.n - tile_base);
+        const uint32_t my_first = warp * (32 * KPT) + lane;  // warp-striped: item r sits at my_first + 32*r
+        KeyT* const    stg      = stage0 + s * TILE;
+
+        // ---- keys (and values) into registers -------------------------------------------------
+#pragma unroll
+        for (int i = 0; i < RADIX / 32; ++i) mywh[lane + 32 * i] = 0;
+        KeyT key[KPT];
+        if (via_tma) {
+            mbar_wait(&mbar[s], (phase_bits >> s) & 1u);
+            phase_bits ^= (1u << s);
+#pragma unroll
+            for (int r = 0; r < KPT; ++r) key[r] = stg[my_first + 32 * r];
+        } else {
+#pragma unroll
+            for (int r = 0; r < KPT; ++r) {
+                const uint32_t i = my_first + 32 * r;
+                key[r]           = (i < valid) ? a.keys_in[tile_base + i] : static_cast<KeyT>(~static_cast<KeyT>(0));
+            }
+        }
+        uint32_t val[HAS_VALS ? KPT : 1];
+        if constexpr (HAS_VALS) {
+#pragma unroll
+            for (int r = 0; r < KPT; ++r) {
+                const uint32_t i = my_first + 32 * r;
+                val[r]           = (i < valid) ? a.vals_in[tile_base + i] : 0u;
+            }
+        }
+        __syncwarp();
+
+        // ---- rank within the warp: match + one counter update per distinct digit ---------------
+        uint32_t rank[KPT];
+#pragma unroll
+        for (int r = 0; r < KPT; ++r) {
+            uint32_t d = digit_of(key[r], ds);
+            if (!is_full && (my_first + 32 * r) >= valid) d = RADIX - 1;  // padding ranks last
+            const uint32_t m      = __match_any_sync(0xffffffffu, d);
+            const uint32_t below  = __popc(m & lt);
+            const int      leader = __ffs(m) - 1;
+            uint32_t       prev   = 0;
+            if (below == 0) prev = atomicAdd(&mywh[d], static_cast<uint32_t>(__popc(m)));
+            __syncwarp();
+            prev    = __shfl_sync(0xffffffffu, prev, leader);
+            rank[r] = prev + below;
+        }
+        __syncthreads();  // (A) all warp counters final; every key of stage[s] is in registers
+
+        // ---- per-digit: scan over warps, publish the tile aggregate, scan over digits ----------
+        const uint32_t chunk          = t / a.tiles_per_chunk;
+        const bool     first_in_chunk = (t % a.tiles_per_chunk) == 0;
+        uint32_t       count = 0, incl = 0;
+        uint32_t*      my_status = a.status + static_cast<size_t>(t) * RADIX + tid;
+        if (tid < RADIX) {
+            uint32_t sum = 0;
+#pragma unroll
+            for (int w = 0; w < NWARPS; ++w) {
+                const uint32_t c       = whist[w * RADIX + tid];
+                whist[w * RADIX + tid] = sum;
+                sum += c;
+            }
+            count = sum;
+            if (!is_full && tid == RADIX - 1) count -= (TILE - valid);
+            st_status(my_status, (first_in_chunk ? STATUS_INCLUSIVE : STATUS_LOCAL) | count);
+            incl = count;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += x;
+            }
+            if (lane == 31) wsum[warp] = incl;
+        }
+        __syncthreads();  // (B)
+        uint32_t local_base = 0;
+        if (tid < RADIX) {
+            uint32_t woff = 0;
+#pragma unroll
+            for (int w = 0; w < RADIX / 32; ++w) woff += (w < warp) ? wsum[w] : 0u;
+            local_base = woff + incl - count;
+#pragma unroll
+            for (int w = 0; w < NWARPS; ++w) whist[w * RADIX + tid] += local_base;
+        }
+        __syncthreads();  // (C) whist[w][d] = tile-local position of warp w's first key with digit d
+
+        // ---- scatter into shared memory in ranked order -----------------------------------------
+#pragma unroll
+        for (int r = 0; r < KPT; ++r) {
+            uint32_t d = digit_of(key[r], ds);
+            if (!is_full && (my_first + 32 * r) >= valid) d = RADIX - 1;
+            const uint32_t pos = mywh[d] + rank[r];
+            stg[pos]           = key[r];
+            if constexpr (HAS_VALS) vstage[pos] = val[r];
+        }
+
+        // ---- decoupled look-back: exclusive prefix of this tile's digit counts in its chunk ----
+        if (tid < RADIX) {
+            unsigned long long excl = 0;
+            if (!first_in_chunk) {
+                const uint32_t* p = my_status - RADIX;
+                while (true) {
+                    const uint32_t v = ld_status(p);
+                    const uint32_t f = v >> 30;
+                    if (f == 0) continue;
+                    excl += v & STATUS_VALUE_MASK;
+                    if (f == 2) break;
+                    p -= RADIX;
+                }
+                st_status(my_status, STATUS_INCLUSIVE | static_cast<uint32_t>(excl + count));
+            }
+            gbase[tid] = a.base[static_cast<size_t>(chunk) * RADIX + tid] + excl - local_base;
+        }
+        __syncthreads();  // (D) staged tile + gbase visible
+
+        // ---- coalesced per-digit runs out to global memory --------------------------------------
+#pragma unroll
+        for (int i = 0; i < KPT; ++i) {
+            const uint32_t p = i * THREADS + tid;
+            if (p < valid) {
+                const KeyT               k   = stg[p];
+                const unsigned long long dst = gbase[digit_of(k, ds)] + p;
+                a.keys_out[dst]              = k;
+                if constexpr (HAS_VALS) a.vals_out[dst] = vstage[p];
+            }
+        }
+        __syncthreads();  // (E) stage[s] free again; sh_tile[s^1] published
+        s ^= 1;
+    }
+}
+
+}  // namespace rsb

@@ -1,0 +1,329 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the oracle, the
+committed golden vectors and numpy (= std::sort / std::stable_sort argsort), bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import KEY_TYPES, numpy_dtype
+
+pytestmark = pytest.mark.gpu
+
+KINDS = ("zeros", "range", "inverted", "uniform", "random")
+SEED = 0x5EED
+SIZES = (1, 2, 3, 31, 33, 100, 1023, 1024, 1025, 4097, 6144, 8192, 8193, 12289, 65536, (1 << 20) + 12345)
+
+
+def host_sort(rsb, gpu, keys, t, with_perm=False, flags=0, perm_in=None):
+    """upload -> sort -> download through rs_sorter_* (the RadixSortGPU call sequence)."""
+    ctx, st = gpu
+    n = len(keys)
+    s = rsb.Sorter(ctx, t, max(n, 1), flags | (rsb.RS_WITH_PERMUTATION if with_perm else 0))
+    try:
+        s.upload(st, keys, perm_in, n)
+        s.sort(st, n)
+        out = np.empty(n, dtype=numpy_dtype(t))
+        perm = np.empty(n, dtype=np.uint32) if with_perm else None
+        s.download(st, out, perm, n)
+        return out, perm, s.download_histograms(st) if n else None
+    finally:
+        s.close()
+
+
+def test_library_is_the_cuda_one(rsb, gpu):
+    ctx, _ = gpu
+    assert ctx.sm_count == 148
+    assert rsb.Context.device_count() >= 1
+
+
+@pytest.mark.parametrize("t", KEY_TYPES)
+@pytest.mark.parametrize("kind", KINDS)
+def test_keys_only_bit_exact(rsb, gpu, oracle, t, kind):
+    for n in SIZES:
+        data = oracle.dataset(kind, t, n, SEED)
+        got, _, hist = host_sort(rsb, gpu, data, t)
+        assert np.array_equal(got, np.sort(data)), (t, kind, n)
+        if n % 1024 == 0:
+            # the reference's OpenCL path restated on the host (needs the padded length)
+            assert np.array_equal(got, oracle.opencl_path(data, t)[0]), (t, kind, n)
+        if n >= 1024 and (n & (n - 1)) == 0:
+            # validity envelope of RadixSortCPU: equal to std::sort for N = 2^k >= 2^10
+            assert np.array_equal(got, oracle.radix_sort_cpu(data, t)), (t, kind, n)
+        # digit histogram read-back: pass p counts byte p of the (sign-flipped) key
+        u = data.view(np.uint32 if data.itemsize == 4 else np.uint64).copy()
+        if t[0] == "i":
+            u ^= u.dtype.type(1) << u.dtype.type(u.itemsize * 8 - 1)
+        assert hist.shape == (data.itemsize, 256)
+        for p in range(data.itemsize):
+            want = np.bincount(((u >> u.dtype.type(8 * p)) & u.dtype.type(255)).astype(np.int64), minlength=256)
+            assert np.array_equal(hist[p].astype(np.int64), want), (t, kind, n, p)
+
+
+@pytest.mark.parametrize("t", KEY_TYPES)
+@pytest.mark.parametrize("kind", KINDS)
+def test_stable_permutation_bit_exact(rsb, gpu, oracle, t, kind):
+    for n in SIZES:
+        data = oracle.dataset(kind, t, n, SEED)
+        got, perm, _ = host_sort(rsb, gpu, data, t, with_perm=True)
+        assert np.array_equal(got, np.sort(data)), (t, kind, n)
+        assert np.array_equal(perm, np.argsort(data, kind="stable").astype(np.uint32)), (t, kind, n)
+        if n % 1024 == 0:
+            k2, p2, _, _ = oracle.opencl_path(data, t, with_perm=True)
+            assert np.array_equal(got, k2) and np.array_equal(perm, p2), (t, kind, n)
+
+
+def test_uploaded_permutation_payload_is_carried(rsb, gpu, oracle):
+    # the reference uploads whatever h_Permut holds (src/RadixSortGPU.cpp:378-386); carry it stably
+    n = 50000
+    data = oracle.dataset("random", "u32", n) & np.uint32(0x3FF)  # many duplicates
+    payload = (np.arange(n, dtype=np.uint32) * np.uint32(2654435761)).astype(np.uint32)
+    got, perm, _ = host_sort(rsb, gpu, data, "u32", with_perm=True, perm_in=payload)
+    order = np.argsort(data, kind="stable")
+    assert np.array_equal(got, data[order]) and np.array_equal(perm, payload[order])
+
+
+@pytest.mark.parametrize("t", KEY_TYPES)
+def test_golden_vectors(rsb, gpu, golden_small, t):
+    for kind in KINDS:
+        data = golden_small[f"in_{kind}_{t}_1024"]
+        got, perm, _ = host_sort(rsb, gpu, data, t, with_perm=True)
+        assert np.array_equal(got, golden_small[f"radixcpu_{kind}_{t}_1024"]), kind
+        assert np.array_equal(got, golden_small[f"stdsort_{kind}_{t}_1024"]), kind
+        assert np.array_equal(data[perm], got)
+
+
+def test_size_sweep_u32_key_value(rsb, gpu, oracle):
+    # BASELINE.json configs[2]: 2^0 .. 2^k sweep of key + stable index (full 2^28 is a property test below)
+    full = oracle.dataset("random", "u32", 1 << 22)
+    for k in range(0, 23):
+        n = 1 << k
+        data = full[:n]
+        got, perm, _ = host_sort(rsb, gpu, data, "u32", with_perm=True)
+        assert np.array_equal(got, np.sort(data)), k
+        assert np.array_equal(perm, np.argsort(data, kind="stable").astype(np.uint32)), k
+
+
+def test_empty_input(rsb, gpu):
+    got, perm, _ = host_sort(rsb, gpu, np.empty(0, dtype=np.uint32), "u32", with_perm=True)
+    assert got.size == 0 and perm.size == 0
+
+
+@pytest.mark.parametrize("t", ("u32", "i64"))
+def test_plain_load_path_matches_tma_path(rsb, gpu, oracle, t):
+    for kind in ("uniform", "range"):
+        data = oracle.dataset(kind, t, 300001, SEED)
+        a, pa, _ = host_sort(rsb, gpu, data, t, with_perm=True)
+        b, pb, _ = host_sort(rsb, gpu, data, t, with_perm=True, flags=rsb.RS_NO_TMA)
+        assert np.array_equal(a, b) and np.array_equal(pa, pb)
+        assert np.array_equal(a, np.sort(data))
+
+
+def test_reference_call_sequence_with_padding(rsb, gpu, oracle):
+    # CRadixSortTask::ComputeGPU (src/CRadixSortTask.cpp:120-130): pad, then upload `rounded` keys whose
+    # tail past N is zero in the host vector; sort `rounded`; compare the first N with the CPU sort of
+    # the same rounded buffer (src/CRadixSortTask.cpp:176-221, 225-244).
+    ctx, st = gpu
+    n = 5000
+    rounded = rsb.round_up_keys(n)
+    host = np.zeros(rounded, dtype=np.int32)
+    host[:n] = oracle.dataset("uniform", "i32", n, SEED)
+    s = rsb.Sorter(ctx, "i32", rounded)
+    s.pad(st, n, rounded)
+    s.upload(st, host, None, rounded)
+    s.sort(st, rounded)
+    out = np.empty(rounded, dtype=np.int32)
+    s.download(st, out, None, rounded)
+    rt = s.runtimes()
+    s.close()
+    assert np.array_equal(out, np.sort(host))
+    assert np.array_equal(out, oracle.opencl_path(host, "i32")[0])
+    assert rt["time_total"]["n"] == 1 and rt["time_paste"]["avg"] == 0.0
+    assert rt["time_total"]["avg"] >= rt["time_reorder"]["avg"] > 0.0
+
+
+def test_pad_value_is_max_minus_one(rsb, gpu):
+    ctx, st = gpu
+    s = rsb.Sorter(ctx, "i64", 2048)
+    host = np.zeros(1000, dtype=np.int64)
+    s.upload(st, host, None, 1000)
+    s.pad(st, 1000, 2048)
+    s.sort(st, 2048)
+    out = np.empty(2048, dtype=np.int64)
+    s.download(st, out, None, 2048)
+    s.close()
+    assert (out[:1000] == 0).all() and (out[1000:] == np.iinfo(np.int64).max - 1).all()
+
+
+# ---- device-pointer entry (torch tensors are only the memory plumbing) -----------------------------
+
+def _torch():
+    import torch
+    return torch
+
+
+def _dev(a):
+    torch = _torch()
+    view = a.view(np.int32 if a.itemsize == 4 else np.int64)
+    return torch.from_numpy(view.copy()).cuda()
+
+
+def _host(tensor, dtype):
+    return tensor.cpu().numpy().view(dtype)
+
+
+@pytest.mark.parametrize("t", KEY_TYPES)
+def test_sort_device_bit_ranges(rsb, gpu, oracle, t):
+    torch = _torch()
+    ctx, st = gpu
+    n = 200003
+    data = oracle.dataset("uniform", t, n, SEED)
+    bits = data.itemsize * 8
+    s = rsb.Sorter(ctx, t, n, rsb.RS_NO_KEY_BUFFERS)
+    d_in = _dev(data)
+    bufs = [torch.empty_like(d_in), torch.empty_like(d_in)]
+    vin = torch.arange(n, dtype=torch.int32, device="cuda")
+    vbufs = [torch.empty_like(vin), torch.empty_like(vin)]
+    torch.cuda.synchronize()
+    u = data.view(np.uint32 if data.itemsize == 4 else np.uint64)
+    for b, e in ((0, bits), (0, 8), (4, 13), (bits - 11, bits), (3, bits - 5), (8, 24)):
+        r = s.sort_device(st, d_in.data_ptr(), bufs[0].data_ptr(), bufs[1].data_ptr(), n, vin.data_ptr(),
+                          vbufs[0].data_ptr(), vbufs[1].data_ptr(), begin_bit=b, end_bit=e)
+        st.sync()
+        got, perm = _host(bufs[r], data.dtype), _host(vbufs[r], np.uint32)
+        sub = (u >> u.dtype.type(b)) & u.dtype.type((1 << (e - b)) - 1)
+        if t[0] == "i" and e == bits:
+            sub = sub ^ (u.dtype.type(1) << u.dtype.type(e - b - 1))
+        order = np.argsort(sub, kind="stable")
+        assert np.array_equal(perm, order.astype(np.uint32)), (t, b, e)
+        assert np.array_equal(got, data[order]), (t, b, e)
+    assert np.array_equal(_host(d_in, data.dtype), data)  # the input buffer is never written
+    s.close()
+
+
+def test_sort_device_unaligned_pointers(rsb, gpu, oracle):
+    torch = _torch()
+    ctx, st = gpu
+    n = 100000
+    data = oracle.dataset("random", "u32", n + 3)
+    s = rsb.Sorter(ctx, "u32", n, rsb.RS_NO_KEY_BUFFERS)
+    d = _dev(data)
+    bufs = [torch.empty(n + 3, dtype=torch.int32, device="cuda") for _ in range(2)]
+    torch.cuda.synchronize()
+    for off in (1, 2, 3):
+        r = s.sort_device(st, d.data_ptr() + 4 * off, bufs[0].data_ptr() + 4 * off, bufs[1].data_ptr() + 4, n)
+        st.sync()
+        got = _host(bufs[r], np.uint32)[(off if r == 0 else 1):][:n]
+        assert np.array_equal(got, np.sort(data[off:off + n])), off
+    s.close()
+
+
+@pytest.mark.parametrize("t", KEY_TYPES)
+def test_device_datasets_closed_forms(rsb, gpu, oracle, t):
+    torch = _torch()
+    ctx, st = gpu
+    n = 70001
+    d = torch.empty(n, dtype=torch.int32 if numpy_dtype(t).itemsize == 4 else torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    for kind in ("zeros", "range", "inverted"):
+        ctx.fill_dataset(st, t, kind, d.data_ptr(), n)
+        st.sync()
+        assert np.array_equal(_host(d, numpy_dtype(t)), oracle.dataset(kind, t, n)), kind
+    # shard semantics: elements [off, off+m) of a larger dataset
+    ctx.fill_dataset(st, t, "inverted", d.data_ptr(), 1000, global_offset=500, total_n=n)
+    st.sync()
+    assert np.array_equal(_host(d, numpy_dtype(t))[:1000], oracle.dataset("inverted", t, n)[500:1500])
+    ctx.fill_dataset(st, t, "uniform", d.data_ptr(), n, seed=7)
+    st.sync()
+    u = _host(d, numpy_dtype(t))
+    info = np.iinfo(numpy_dtype(t))
+    assert u[0] == info.max and u[-1] == info.min and len(np.unique(u)) > n * 0.99
+    ctx.fill_dataset(st, t, "random", d.data_ptr(), n, seed=7)
+    st.sync()
+    r = _host(d, numpy_dtype(t))
+    if numpy_dtype(t).itemsize == 8:
+        assert int(r.max()) < 2**32 and int(r.min()) >= 0  # 32-bit values zero-extended, like Random<T>
+
+
+def test_check_kernels_detect_errors(rsb, gpu, oracle):
+    torch = _torch()
+    ctx, st = gpu
+    n = 100000
+    data = np.sort(oracle.dataset("uniform", "i32", n, SEED))
+    d = _dev(data)
+    torch.cuda.synchronize()
+    ok = ctx.check(st, "i32", d.data_ptr(), n)
+    assert ok["unordered"] == 0 and ok["sum"] == int(data.view(np.uint32).astype(np.uint64).sum())
+    bad = data.copy()
+    bad[[10, 5000]] = bad[[5000, 10]]
+    d2 = _dev(bad)
+    torch.cuda.synchronize()
+    res = ctx.check(st, "i32", d2.data_ptr(), n)
+    assert res["unordered"] >= 1 and res["hash_sum"] == ok["hash_sum"] and res["hash_xor"] == ok["hash_xor"]
+    bad[7] ^= 1
+    d3 = _dev(bad)
+    torch.cuda.synchronize()
+    res = ctx.check(st, "i32", d3.data_ptr(), n)
+    assert res["hash_sum"] != ok["hash_sum"]
+    # lower bound
+    q = np.array([np.iinfo(np.int32).min, -5, 0, 77, np.iinfo(np.int32).max], dtype=np.int32)
+    dq = _dev(q)
+    out = torch.empty(len(q), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.lower_bound(st, "i32", d.data_ptr(), n, dq.data_ptr(), len(q), out.data_ptr())
+    st.sync()
+    assert np.array_equal(out.cpu().numpy(), np.searchsorted(data, q, side="left"))
+
+
+# ---- BASELINE.json full sizes: size-independent properties, everything resident on the device -------
+
+def _full_size_case(rsb, gpu, t, kind, n, with_perm):
+    torch = _torch()
+    ctx, st = gpu
+    tdt = torch.int32 if numpy_dtype(t).itemsize == 4 else torch.int64
+    d_in = torch.empty(n, dtype=tdt, device="cuda")
+    bufs = [torch.empty(n, dtype=tdt, device="cuda") for _ in range(2)]
+    vin = vb = None
+    if with_perm:
+        vin = torch.arange(n, dtype=torch.int32, device="cuda")  # wraps past 2^31 harmlessly: n <= 2^28 here
+        vb = [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(2)]
+    torch.cuda.synchronize()
+    ctx.fill_dataset(st, t, kind, d_in.data_ptr(), n, seed=SEED)
+    s = rsb.Sorter(ctx, t, n, rsb.RS_NO_KEY_BUFFERS)
+    r = s.sort_device(st, d_in.data_ptr(), bufs[0].data_ptr(), bufs[1].data_ptr(), n,
+                      vin.data_ptr() if with_perm else None, vb[0].data_ptr() if with_perm else None,
+                      vb[1].data_ptr() if with_perm else None)
+    st.sync()
+    before = ctx.check(st, t, d_in.data_ptr(), n)
+    after = ctx.check(st, t, bufs[r].data_ptr(), n)
+    # sorted + same multiset  =>  the unique sorted arrangement, i.e. bit-exact with std::sort
+    assert after["unordered"] == 0, (t, kind)
+    assert {k: after[k] for k in ("sum", "hash_sum", "hash_xor")} == {k: before[k] for k in ("sum", "hash_sum", "hash_xor")}
+    if kind in ("range", "inverted"):
+        # closed form: both sort to Range; compare fingerprints with a generated Range
+        ctx.fill_dataset(st, t, "range", bufs[1 - r].data_ptr(), n)
+        want = ctx.check(st, t, bufs[1 - r].data_ptr(), n)
+        assert want == after
+    if with_perm:
+        res = ctx.check_permutation(st, t, d_in.data_ptr(), bufs[r].data_ptr(), vb[r].data_ptr(), n)
+        assert res == {"mismatches": 0, "unstable": 0}, (t, kind)
+    s.close()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_full_size_2_28_u32_keys(rsb, gpu, kind):
+    _full_size_case(rsb, gpu, "u32", kind, 1 << 28, with_perm=False)      # configs[1]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_full_size_2_28_u32_key_value(rsb, gpu, kind):
+    _full_size_case(rsb, gpu, "u32", kind, 1 << 28, with_perm=True)       # configs[2]
+
+
+@pytest.mark.parametrize("t", ("i32", "u64", "i64"))
+@pytest.mark.parametrize("kind", ("uniform", "inverted", "random"))
+def test_full_size_2_28_other_types(rsb, gpu, t, kind):
+    _full_size_case(rsb, gpu, t, kind, 1 << 28, with_perm=False)          # configs[3]
+
+
+def test_more_than_one_lookback_chunk(rsb, gpu):
+    # > 2^30 keys: the look-back chain restarts at a chunk boundary with offsets from the chunk histograms
+    _full_size_case(rsb, gpu, "u32", "uniform", (1 << 30) + 77777, with_perm=False)
+    _full_size_case(rsb, gpu, "u32", "zeros", (1 << 30) + 8192 * 3 + 1, with_perm=False)
