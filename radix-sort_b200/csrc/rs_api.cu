@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -130,17 +131,20 @@ static Plan make_plan(uint64_t n, size_t key_bytes, bool has_vals, int passes) {
     p.tile            = tile_keys(key_bytes, has_vals);
     p.num_tiles       = (n + p.tile - 1) / p.tile;
     p.tiles_per_chunk = static_cast<uint32_t>(CHUNK_MAX_KEYS / p.tile);
+    // test hook: shrink the look-back chunk so the multi-chunk path can be checked exactly at small n
+    static const long debug_tpc = [] { const char* e = getenv("RSB200_DEBUG_TILES_PER_CHUNK"); return e ? atol(e) : 0L; }();
+    if (debug_tpc > 0 && static_cast<uint64_t>(debug_tpc) < p.tiles_per_chunk) p.tiles_per_chunk = static_cast<uint32_t>(debug_tpc);
     p.chunk_keys      = static_cast<uint64_t>(p.tiles_per_chunk) * p.tile;
     p.num_chunks      = static_cast<int>((n + p.chunk_keys - 1) / p.chunk_keys);
     if (p.num_chunks < 1) p.num_chunks = 1;
     p.passes          = passes;
     auto align = [](size_t x) { return (x + 255) & ~static_cast<size_t>(255); };
     size_t o     = 0;
-    p.off_hist   = o; o = align(o + sizeof(uint64_t) * passes * p.num_chunks * RADIX);
+    p.off_hist   = o; o = align(o + sizeof(uint64_t) * passes * RADIX);
     p.off_ctr    = o; o = align(o + sizeof(uint32_t) * MAX_PASSES);
+    p.off_base   = o; o = align(o + sizeof(uint64_t) * passes * p.num_chunks * RADIX);
     p.off_status = o; o = align(o + sizeof(uint32_t) * RADIX * p.num_tiles * passes);
     p.zero_bytes = o;
-    p.off_base   = o; o = align(o + sizeof(uint64_t) * passes * p.num_chunks * RADIX);
     p.total      = o;
     return p;
 }
@@ -148,15 +152,18 @@ static Plan make_plan(uint64_t n, size_t key_bytes, bool has_vals, int passes) {
 template <typename KeyT, int NPASS>
 static cudaError_t launch_hist_n(int grid, cudaStream_t st, const KeyT* keys, uint64_t n, const Plan& pl,
                                  unsigned long long* hist, const PassTable& pt) {
-    rs_histogram_kernel<KeyT, NPASS><<<grid, HIST_THREADS, 0, st>>>(keys, n, pl.chunk_keys, pl.num_chunks, hist, pt);
+    rs_histogram_kernel<KeyT, NPASS><<<grid, HIST_THREADS, 0, st>>>(keys, n, hist, pt);
     return cudaGetLastError();
 }
 template <typename KeyT>
 static cudaError_t launch_hist(int sm_count, cudaStream_t st, const KeyT* keys, uint64_t n, const Plan& pl,
                                unsigned long long* hist, const PassTable& pt) {
     const uint64_t vec_per_block = static_cast<uint64_t>(HIST_THREADS) * HIST_VECS * (16 / sizeof(KeyT));
-    uint64_t want = (std::min<uint64_t>(n, pl.chunk_keys) + vec_per_block - 1) / vec_per_block;
-    int grid = static_cast<int>(std::min<uint64_t>(std::max<uint64_t>(want, 1), static_cast<uint64_t>(sm_count) * 4));
+    uint64_t want = (n + vec_per_block - 1) / vec_per_block;
+    // a block's shared-memory counters are 32-bit: keep every block below 2^31 keys
+    const uint64_t min_grid = (n >> 31) + 1;
+    int grid = static_cast<int>(std::max<uint64_t>(
+        min_grid, std::min<uint64_t>(std::max<uint64_t>(want, 1), static_cast<uint64_t>(sm_count) * 4)));
     switch (pt.num_passes) {
         case 1: return launch_hist_n<KeyT, 1>(grid, st, keys, n, pl, hist, pt);
         case 2: return launch_hist_n<KeyT, 2>(grid, st, keys, n, pl, hist, pt);
@@ -255,6 +262,7 @@ static int sort_typed(rs_sorter s, cudaStream_t st, const KeyT* in, KeyT* buf0, 
         a.counter         = ctr + p;
         a.num_tiles       = static_cast<uint32_t>(pl.num_tiles);
         a.tiles_per_chunk = pl.tiles_per_chunk;
+        a.num_chunks      = static_cast<uint32_t>(pl.num_chunks);
         a.digit           = pt.d[p];
         a.use_tma = ((s->flags & RS_NO_TMA) == 0) && ((reinterpret_cast<uintptr_t>(a.keys_in) & 15u) == 0);
         cudaError_t e = has_vals ? launch_pass<KeyT, true>(s->ctx, st, a) : launch_pass<KeyT, false>(s->ctx, st, a);
@@ -689,20 +697,13 @@ int rs_sorter_download(rs_sorter s, rs_stream st, void* h_keys_out, uint32_t* h_
 int rs_sorter_download_histograms(rs_sorter s, rs_stream st, uint64_t* h_hist, size_t capacity, int* passes) {
     if (!s || !st || !h_hist) return fail(RS_DATA_DOWNLOAD_FAILED, "null argument");
     RS_CUDA(cudaSetDevice(s->ctx->device), RS_DATA_DOWNLOAD_FAILED);
-    const int P = s->last_passes, C = s->last_chunks;
+    const int P = s->last_passes;
     if (passes) *passes = P;
     if (P == 0) return RS_OK;
     if (capacity < static_cast<size_t>(P) * RADIX) return fail(RS_HOST_BUFFERS_FAILED, "histogram buffer too small");
-    std::vector<uint64_t> tmp(static_cast<size_t>(P) * C * RADIX);
-    RS_CUDA(cudaMemcpyAsync(tmp.data(), s->scratch + s->last_hist_offset, tmp.size() * sizeof(uint64_t),
+    RS_CUDA(cudaMemcpyAsync(h_hist, s->scratch + s->last_hist_offset, static_cast<size_t>(P) * RADIX * sizeof(uint64_t),
                             cudaMemcpyDeviceToHost, st->st), RS_DATA_DOWNLOAD_FAILED);
     RS_CUDA(cudaStreamSynchronize(st->st), RS_DATA_DOWNLOAD_FAILED);
-    for (int p = 0; p < P; ++p)
-        for (int d = 0; d < RADIX; ++d) {
-            uint64_t sum = 0;
-            for (int c = 0; c < C; ++c) sum += tmp[(static_cast<size_t>(p) * C + c) * RADIX + d];
-            h_hist[static_cast<size_t>(p) * RADIX + d] = sum;
-        }
     return RS_OK;
 }
 

@@ -12,8 +12,9 @@
 //
 // Data layout in HBM (all owned by rs_sorter, see rs_api.cu):
 //   keys   : T[n] ping-pong pair           values : uint32[n] ping-pong pair (optional)
-//   hist   : uint64[passes][chunks][256]   digit counts per lookback chunk
-//   base   : uint64[passes][chunks][256]   global output offset of (chunk, digit)
+//   hist   : uint64[passes][256]           digit counts of the whole input (order-independent)
+//   base   : uint64[passes][chunks][256]   bit 63 = ready | global output offset of (chunk, digit);
+//                                          chunk 0 from rs_scan_kernel, chunk c+1 from the last tile of chunk c
 //   status : uint32[passes][tiles][256]    2 flag bits | 30-bit count  (look-back words)
 //   ctr    : uint32[passes]                dynamic tile-id dispensers
 #pragma once
@@ -29,6 +30,7 @@ constexpr uint32_t STATUS_INCLUSIVE  = 2u << 30;   // inclusive prefix (within c
 constexpr uint32_t STATUS_VALUE_MASK = (1u << 30) - 1u;
 constexpr uint64_t CHUNK_MAX_KEYS    = (1ull << 30) - 1ull;  // a look-back chain never sums past this
 constexpr int      MAX_PASSES        = 8;
+constexpr unsigned long long BASE_READY = 1ull << 63;      // ready flag of a chunk-base word
 
 struct DigitSpec {
     int      shift;  // first bit of the digit
@@ -97,6 +99,14 @@ __device__ __forceinline__ uint32_t ld_status(const uint32_t* p) {
 __device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long ld_base(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_base(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -149,87 +159,75 @@ __device__ __forceinline__ void hist_accumulate_row(uint32_t* sh, const KeyT (&k
 
 template <typename KeyT, int NPASS>
 __global__ void __launch_bounds__(HIST_THREADS)
-rs_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, uint64_t chunk_keys, int num_chunks,
-                    unsigned long long* __restrict__ hist /* [NPASS][num_chunks][256] */, PassTable pt) {
+rs_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ hist /* [NPASS][256] */,
+                    PassTable pt) {
     constexpr int KV = 16 / sizeof(KeyT);
     __shared__ uint32_t sh[NPASS * RADIX];
     const int  tid     = threadIdx.x;
     const int  lane    = tid & 31;
     const bool aligned = (reinterpret_cast<uintptr_t>(keys) & 15u) == 0;
 
-    for (int c = 0; c < num_chunks; ++c) {
-        for (int i = tid; i < NPASS * RADIX; i += HIST_THREADS) sh[i] = 0;
-        __syncthreads();
-        const uint64_t cbeg = static_cast<uint64_t>(c) * chunk_keys;
-        const uint64_t cend = (cbeg + chunk_keys < n) ? cbeg + chunk_keys : n;
-        const uint64_t cnt  = cend - cbeg;
-        const KeyT*    ck   = keys + cbeg;  // chunk_keys is a multiple of the tile size => keeps 16B alignment
-        const uint64_t nvec = aligned ? cnt / KV : 0;
-        const uint4*   cv   = reinterpret_cast<const uint4*>(ck);
+    for (int i = tid; i < NPASS * RADIX; i += HIST_THREADS) sh[i] = 0;
+    __syncthreads();
+    const uint64_t nvec = aligned ? n / KV : 0;
+    const uint4*   cv   = reinterpret_cast<const uint4*>(keys);
 
-        // whole warps walk the vector range so the warp-uniform shortcut sees full rows
-        const uint64_t stride = static_cast<uint64_t>(gridDim.x) * HIST_THREADS;
-        const uint64_t first  = static_cast<uint64_t>(blockIdx.x) * HIST_THREADS + tid;
-        const uint64_t rounds = (nvec + stride * HIST_VECS - 1) / (stride * HIST_VECS);
-        for (uint64_t r = 0; r < rounds; ++r) {
-            uint4 v[HIST_VECS];
-            bool  act[HIST_VECS];
+    // whole warps walk the vector range so the warp-uniform shortcut sees full rows; a block never counts
+    // more than 2^32 keys (grid >= n / 2^31 is guaranteed by the launcher)
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * HIST_THREADS;
+    const uint64_t first  = static_cast<uint64_t>(blockIdx.x) * HIST_THREADS + tid;
+    const uint64_t rounds = (nvec + stride * HIST_VECS - 1) / (stride * HIST_VECS);
+    for (uint64_t r = 0; r < rounds; ++r) {
+        uint4 v[HIST_VECS];
+        bool  act[HIST_VECS];
 #pragma unroll
-            for (int u = 0; u < HIST_VECS; ++u) {
-                const uint64_t idx = first + (r * HIST_VECS + u) * stride;
-                act[u]             = idx < nvec;
-                v[u]               = act[u] ? __ldg(cv + idx) : make_uint4(0, 0, 0, 0);
-            }
+        for (int u = 0; u < HIST_VECS; ++u) {
+            const uint64_t idx = first + (r * HIST_VECS + u) * stride;
+            act[u]             = idx < nvec;
+            v[u]               = act[u] ? __ldg(cv + idx) : make_uint4(0, 0, 0, 0);
+        }
 #pragma unroll
-            for (int u = 0; u < HIST_VECS; ++u) {
-                KeyT k[KV];
-                if constexpr (sizeof(KeyT) == 4) {
-                    k[0]      = static_cast<KeyT>(v[u].x);
-                    k[1 % KV] = static_cast<KeyT>(v[u].y);
-                    k[2 % KV] = static_cast<KeyT>(v[u].z);
-                    k[3 % KV] = static_cast<KeyT>(v[u].w);
-                } else {
-                    k[0]      = static_cast<KeyT>((static_cast<uint64_t>(v[u].y) << 32) | v[u].x);
-                    k[1 % KV] = static_cast<KeyT>((static_cast<uint64_t>(v[u].w) << 32) | v[u].z);
-                }
-                hist_accumulate_row<KeyT, NPASS>(sh, k, act[u], pt, lane);
+        for (int u = 0; u < HIST_VECS; ++u) {
+            KeyT k[KV];
+            if constexpr (sizeof(KeyT) == 4) {
+                k[0]      = static_cast<KeyT>(v[u].x);
+                k[1 % KV] = static_cast<KeyT>(v[u].y);
+                k[2 % KV] = static_cast<KeyT>(v[u].z);
+                k[3 % KV] = static_cast<KeyT>(v[u].w);
+            } else {
+                k[0]      = static_cast<KeyT>((static_cast<uint64_t>(v[u].y) << 32) | v[u].x);
+                k[1 % KV] = static_cast<KeyT>((static_cast<uint64_t>(v[u].w) << 32) | v[u].z);
             }
+            hist_accumulate_row<KeyT, NPASS>(sh, k, act[u], pt, lane);
         }
-        // scalar tail (and the whole chunk when the base pointer is not 16-byte aligned)
-        for (uint64_t i = nvec * KV + first; i < cnt; i += stride) {
-            const KeyT k = ck[i];
+    }
+    // scalar tail (and everything when the base pointer is not 16-byte aligned)
+    for (uint64_t i = nvec * KV + first; i < n; i += stride) {
+        const KeyT k = keys[i];
 #pragma unroll
-            for (int p = 0; p < NPASS; ++p) atomicAdd(&sh[p * RADIX + digit_of(k, pt.d[p])], 1u);
-        }
-        __syncthreads();
-        for (int i = tid; i < NPASS * RADIX; i += HIST_THREADS) {
-            const uint32_t v = sh[i];
-            if (v) {
-                const int p = i / RADIX, d = i % RADIX;
-                atomicAdd(&hist[(static_cast<size_t>(p) * num_chunks + c) * RADIX + d],
-                          static_cast<unsigned long long>(v));
-            }
-        }
-        __syncthreads();
+        for (int p = 0; p < NPASS; ++p) atomicAdd(&sh[p * RADIX + digit_of(k, pt.d[p])], 1u);
+    }
+    __syncthreads();
+    for (int i = tid; i < NPASS * RADIX; i += HIST_THREADS) {
+        const uint32_t v = sh[i];
+        if (v) atomicAdd(&hist[i], static_cast<unsigned long long>(v));
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Digit-offset scan: one block per pass.  base[p][c][d] = #keys with digit < d (all chunks)
-//                                                       + #keys with digit d in chunks < c.
+// Digit-offset scan: one block per pass.  base[p][0][d] = READY | #keys with digit < d.
 // Replaces scanhistograms x2 + pastehistograms of the reference for the GLOBAL part; the per-tile
-// part is the look-back inside rs_onesweep_kernel.
+// part is the look-back inside rs_onesweep_kernel.  Chunks > 0 (inputs past 2^30 keys) get their
+// base from the last tile of the previous chunk; their words stay 0 (= not ready) here.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RADIX)
 rs_scan_kernel(const unsigned long long* __restrict__ hist, unsigned long long* __restrict__ base, int num_chunks) {
     __shared__ unsigned long long wsum[RADIX / 32];
-    const int    p    = blockIdx.x;
-    const int    d    = threadIdx.x;
-    const int    lane = d & 31, warp = d >> 5;
-    const size_t row  = static_cast<size_t>(p) * num_chunks * RADIX;
-    unsigned long long total = 0;
-    for (int c = 0; c < num_chunks; ++c) total += hist[row + static_cast<size_t>(c) * RADIX + d];
-    unsigned long long incl = total;
+    const int p    = blockIdx.x;
+    const int d    = threadIdx.x;
+    const int lane = d & 31, warp = d >> 5;
+    const unsigned long long total = hist[static_cast<size_t>(p) * RADIX + d];
+    unsigned long long       incl  = total;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -239,11 +237,7 @@ rs_scan_kernel(const unsigned long long* __restrict__ hist, unsigned long long* 
     __syncthreads();
     unsigned long long woff = 0;
     for (int w = 0; w < warp; ++w) woff += wsum[w];
-    unsigned long long run = woff + incl - total;
-    for (int c = 0; c < num_chunks; ++c) {
-        base[row + static_cast<size_t>(c) * RADIX + d] = run;
-        run += hist[row + static_cast<size_t>(c) * RADIX + d];
-    }
+    base[static_cast<size_t>(p) * num_chunks * RADIX + d] = BASE_READY | (woff + incl - total);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -261,11 +255,12 @@ struct OnesweepArgs {
     const uint32_t*           vals_in;
     uint32_t*                 vals_out;
     uint64_t                  n;
-    const unsigned long long* base;    // [chunks][256] for this pass
+    unsigned long long*       base;    // [chunks][256] for this pass: READY | offset (chunks > 0 zeroed)
     uint32_t*                 status;  // [tiles][256] for this pass, zeroed
     uint32_t*                 counter; // tile-id dispenser for this pass, zeroed
     uint32_t                  num_tiles;
     uint32_t                  tiles_per_chunk;
+    uint32_t                  num_chunks;
     DigitSpec                 digit;
     int                       use_tma;
 };
@@ -453,7 +448,15 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
                 }
                 st_status(my_status, STATUS_INCLUSIVE | static_cast<uint32_t>(excl + count));
             }
-            gbase[tid] = a.base[static_cast<size_t>(chunk) * RADIX + tid] + excl - local_base;
+            // global offset of this chunk's first key with this digit (ready at once for chunk 0)
+            unsigned long long* cb_ptr = a.base + static_cast<size_t>(chunk) * RADIX + tid;
+            unsigned long long  cb;
+            do { cb = ld_base(cb_ptr); } while (!(cb & BASE_READY));
+            cb &= ~BASE_READY;
+            // the last tile of a chunk hands the next chunk its base (its inclusive prefix = the chunk's counts)
+            if ((t % a.tiles_per_chunk) == a.tiles_per_chunk - 1 && chunk + 1 < a.num_chunks)
+                st_base(cb_ptr + RADIX, BASE_READY | (cb + excl + count));
+            gbase[tid] = cb + excl - local_base;
         }
         __syncthreads();  // (D) staged tile + gbase visible
 
