@@ -106,7 +106,7 @@ struct TileCfg;
 template <> struct TileCfg<uint32_t, false> { static constexpr int THREADS = 512, KPT = 16, MINB = 2; };
 template <> struct TileCfg<uint32_t, true>  { static constexpr int THREADS = 512, KPT = 12, MINB = 2; };
 template <> struct TileCfg<uint64_t, false> { static constexpr int THREADS = 512, KPT = 8,  MINB = 2; };
-template <> struct TileCfg<uint64_t, true>  { static constexpr int THREADS = 512, KPT = 6,  MINB = 2; };
+template <> struct TileCfg<uint64_t, true>  { static constexpr int THREADS = 512, KPT = 8,  MINB = 2; };
 
 static int tile_keys(size_t key_bytes, bool has_vals) {
     if (key_bytes == 4) return has_vals ? TileCfg<uint32_t, true>::THREADS * TileCfg<uint32_t, true>::KPT

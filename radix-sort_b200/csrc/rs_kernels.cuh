@@ -31,6 +31,23 @@ constexpr uint32_t STATUS_INCLUSIVE  = 2u << 30;   // inclusive prefix (within c
 constexpr uint32_t STATUS_VALUE_MASK = (1u << 30) - 1u;
 constexpr uint64_t CHUNK_MAX_KEYS    = (1ull << 30) - 1ull;  // a look-back chain never sums past this
 constexpr int      MAX_PASSES        = 8;
+#ifndef RS_LB_WINDOW
+#define RS_LB_WINDOW 4
+#endif
+constexpr int      LB_WINDOW         = RS_LB_WINDOW;  // look-back status words in flight per thread
+// Ranking primitive (see the measurements quoted above rs_onesweep_kernel):
+//   0 = eight ballots build the match mask (VOTE pipe), one counter update per distinct digit
+//   1 = shared-memory lane bitmap (LSU pipe)
+#ifndef RS_RANK_MODE
+#define RS_RANK_MODE 1
+#endif
+#if RS_RANK_MODE == 0
+using WEntry = uint32_t;                       // [warp][digit] running count
+#define RS_W_CNT(e) (e)
+#else
+using WEntry = uint2;                          // [warp][digit] {lane bitmap, running count}
+#define RS_W_CNT(e) ((e).y)
+#endif
 constexpr unsigned long long BASE_READY = 1ull << 63;      // ready flag of a chunk-base word
 
 struct DigitSpec {
@@ -108,6 +125,9 @@ __device__ __forceinline__ unsigned long long ld_base(const unsigned long long* 
 __device__ __forceinline__ void st_base(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// Staging-buffer swizzle: sorted inputs (Range, Inverted Range) scatter with a power-of-two stride
+// (one run per digit, equal lengths), which would put all 32 lanes of a row on one bank.
+__device__ __forceinline__ uint32_t swz(uint32_t pos) { return pos ^ ((pos >> 5) & 31u); }
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -282,7 +302,7 @@ struct OnesweepSmem {
     static constexpr size_t off_stage1  = off_stage0 + stage_bytes;
     static constexpr size_t off_vstage  = off_stage1 + stage_bytes;
     static constexpr size_t off_wtab    = off_vstage + (HAS_VALS ? sizeof(uint32_t) * TILE : 0);
-    static constexpr size_t off_kptr    = off_wtab + sizeof(uint2) * NWARPS * RADIX;
+    static constexpr size_t off_kptr    = off_wtab + sizeof(WEntry) * NWARPS * RADIX;
     static constexpr size_t off_vptr    = off_kptr + sizeof(void*) * RADIX;
     static constexpr size_t off_wsum    = off_vptr + (HAS_VALS ? sizeof(void*) * RADIX : 0);
     static constexpr size_t off_mbar    = off_wsum + sizeof(uint32_t) * 16;
@@ -302,7 +322,7 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     KeyT* const        stage0  = reinterpret_cast<KeyT*>(smem_raw + L::off_stage0);  // stage s = stage0 + s*TILE
     uint32_t* const    vstage  = reinterpret_cast<uint32_t*>(smem_raw + L::off_vstage);
-    uint2* const       wtab    = reinterpret_cast<uint2*>(smem_raw + L::off_wtab);   // [warp][digit] {bitmap, count}
+    WEntry* const      wtab    = reinterpret_cast<WEntry*>(smem_raw + L::off_wtab);  // [warp][digit]
     KeyT** const       kptr    = reinterpret_cast<KeyT**>(smem_raw + L::off_kptr);   // [digit] -> keys_out run - tile pos
     uint32_t** const   vptr    = reinterpret_cast<uint32_t**>(smem_raw + L::off_vptr);
     uint32_t* const    wsum    = reinterpret_cast<uint32_t*>(smem_raw + L::off_wsum);
@@ -316,7 +336,7 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
     const uint32_t  lane_bit = 1u << lane;
     const DigitSpec ds       = a.digit;
     const uint32_t  full_tiles = static_cast<uint32_t>(a.n / TILE);  // tiles [0, full_tiles) are complete
-    uint2* const    wt       = wtab + warp * RADIX;
+    WEntry* const   wt       = wtab + warp * RADIX;
 
     auto issue_prefetch = [&](uint32_t t, int s) {
         // thread 0 only: bulk copy of a complete tile into stage s
@@ -338,7 +358,7 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
     }
     // the warp tables start clean; every tile leaves its bitmaps clear and re-zeroes the counts itself
 #pragma unroll
-    for (int i = 0; i < RADIX / 32; ++i) wt[lane + 32 * i] = make_uint2(0u, 0u);
+    for (int i = 0; i < RADIX / 32; ++i) wt[lane + 32 * i] = WEntry{};
     __syncthreads();
 
     uint32_t phase_bits = 0;  // bit s = parity to wait for on mbar[s]
@@ -383,6 +403,23 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
             if (!FULL && (my_first + 32 * r) >= valid) d = RADIX - 1;  // padding ranks last
             int all_same;
             __match_all_sync(0xffffffffu, d, &all_same);
+#if RS_RANK_MODE == 0
+            uint32_t m = 0xffffffffu;
+            if (!all_same) {  // warp-uniform branch
+#pragma unroll
+                for (int b = 0; b < RADIX_BITS; ++b) {
+                    const bool     bit = (d >> b) & 1u;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+                    m &= bit ? bal : ~bal;
+                }
+            }
+            const uint32_t below  = __popc(m & lt);
+            const int      leader = __ffs(m) - 1;
+            uint32_t       prev   = 0;
+            if (below == 0) prev = atomicAdd(&wt[d], static_cast<uint32_t>(__popc(m)));  // lowest lane of the group
+            prev    = __shfl_sync(0xffffffffu, prev, leader);
+            rank[r] = prev + below;
+#else
             if (all_same) {  // warp-uniform: 32 equal digits, ranks follow the lane order
                 const uint32_t c = wt[d].y;
                 __syncwarp();
@@ -397,6 +434,7 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
                 if (below == 0) wt[d] = make_uint2(0u, e.y + __popc(e.x));  // lowest lane of the group
                 rank[r] = e.y + below;
             }
+#endif
             __syncwarp();
         }
         __syncthreads();  // (A) all warp counts final; every key of this stage is in registers
@@ -410,8 +448,8 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
             uint32_t sum = 0;
 #pragma unroll
             for (int w = 0; w < NWARPS; ++w) {
-                const uint32_t c         = wtab[w * RADIX + tid].y;
-                wtab[w * RADIX + tid].y  = sum;
+                const uint32_t c                 = RS_W_CNT(wtab[w * RADIX + tid]);
+                RS_W_CNT(wtab[w * RADIX + tid]) = sum;
                 sum += c;
             }
             count = sum;
@@ -433,7 +471,7 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
             for (int w = 0; w < RADIX / 32; ++w) woff += (w < warp) ? wsum[w] : 0u;
             local_base = woff + incl - count;
 #pragma unroll
-            for (int w = 0; w < NWARPS; ++w) wtab[w * RADIX + tid].y += local_base;
+            for (int w = 0; w < NWARPS; ++w) RS_W_CNT(wtab[w * RADIX + tid]) += local_base;
         }
         __syncthreads();  // (C) wtab[w][d].y = tile-local position of warp w's first key with digit d
 
@@ -442,23 +480,34 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
         for (int r = 0; r < KPT; ++r) {
             uint32_t d = digit_of(key[r], ds);
             if (!FULL && (my_first + 32 * r) >= valid) d = RADIX - 1;
-            const uint32_t pos = wt[d].y + rank[r];
-            stg[pos]           = key[r];
-            if constexpr (HAS_VALS) vstage[pos] = val[r];
+            const uint32_t pos = RS_W_CNT(wt[d]) + rank[r];
+            stg[swz(pos)]      = key[r];
+            if constexpr (HAS_VALS) vstage[swz(pos)] = val[r];
         }
 
         // ---- decoupled look-back: exclusive prefix of this tile's digit counts in its chunk ----
         if (tid < RADIX) {
             unsigned long long excl = 0;
             if (!first_in_chunk) {
-                const uint32_t* p = my_status - RADIX;
-                while (true) {
-                    const uint32_t v = ld_status(p);
-                    const uint32_t f = v >> 30;
-                    if (f == 0) continue;
-                    excl += v & STATUS_VALUE_MASK;
-                    if (f == 2) break;
-                    p -= RADIX;
+                // walk back over the predecessors of this chunk, LB_WINDOW status words per round trip
+                int32_t        left = static_cast<int32_t>(t % a.tiles_per_chunk);  // predecessors in this chunk
+                const uint32_t* p   = my_status - RADIX;
+                bool           done = false;
+                while (!done) {
+                    uint32_t v[LB_WINDOW];
+#pragma unroll
+                    for (int j = 0; j < LB_WINDOW; ++j)
+                        v[j] = (j < left) ? ld_status(p - j * RADIX) : STATUS_INCLUSIVE;  // before the chunk: prefix 0
+#pragma unroll
+                    for (int j = 0; j < LB_WINDOW; ++j) {
+                        if (done) break;
+                        const uint32_t f = v[j] >> 30;
+                        if (f == 0) break;  // not published yet: re-read from here
+                        excl += v[j] & STATUS_VALUE_MASK;
+                        p -= RADIX;
+                        --left;
+                        if (f == 2) done = true;
+                    }
                 }
                 st_status(my_status, STATUS_INCLUSIVE | static_cast<uint32_t>(excl + count));
             }
@@ -479,15 +528,15 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
 
         // ---- coalesced per-digit runs out to global memory; re-zero the warp counts -------------
 #pragma unroll
-        for (int i = 0; i < RADIX / 32; ++i) wt[lane + 32 * i].y = 0u;
+        for (int i = 0; i < RADIX / 32; ++i) RS_W_CNT(wt[lane + 32 * i]) = 0u;
 #pragma unroll
         for (int i = 0; i < KPT; ++i) {
             const uint32_t p = i * THREADS + tid;
             if (FULL || p < valid) {
-                const KeyT     k = stg[p];
+                const KeyT     k = stg[swz(p)];
                 const uint32_t d = digit_of(k, ds);
                 kptr[d][p]       = k;
-                if constexpr (HAS_VALS) vptr[d][p] = vstage[p];
+                if constexpr (HAS_VALS) vptr[d][p] = vstage[swz(p)];
             }
         }
         __syncthreads();  // (E) stage free again; sh_tile[s^1] published
