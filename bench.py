@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py -- the contract bench of the B200 radix sort (one JSON line on stdout, rank 0).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dataset uniform]
+  N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N
+
+A "step" is one complete sort of the workload through the hot path:
+  N = 1 : 2^28 uint32 keys, keys-only (BASELINE.json configs[1]), dataset `--dataset` (default: uniform),
+          inputs resident in HBM; every step re-sorts the same unsorted input (the sort never writes it);
+          1 GiB in / 1 GiB out per pass, far larger than the 126 MB L2.
+  N > 1 : 2^33 uint32 keys in total (configs[4]; strong scaling over N = 2, 4, 8), generated on the
+          devices per shard; a step = local onesweep + splitter all-reduce + NCCL all-to-all + final sort.
+`value` is whole-job Gkeys/s (keys of all ranks / max-over-ranks device time, CUDA events).
+`e2e` runs the same metric through the reference-facing call sequence of the C ABI
+(rs_sorter_upload -> rs_sorter_sort -> rs_sorter_download, pinned HOST buffers; copies inside the timing).
+`roofline` is the dominant kernel (one onesweep pass): algorithmic bytes 2*sizeof(key)*n per launch over the
+kernel's event-timed duration, against MEASURED_PEAKS.json's hbm_gbs.
+`cpu_baseline` times the reference's own RadixSortCPU (oracle/_ref, unmodified reference headers; falls back to
+the C restatement in oracle/) on the host, single thread (the reference is single-threaded), on a bounded sample.
+`--impl reference` prints the same line for that CPU implementation alone.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Gkeys/s sorting 2^28 uint32 keys"
+UNIT = "Gkeys/s"
+LOG2_SINGLE = 28
+LOG2_DIST_TOTAL = 33
+KEY_TYPE = "u32"
+KEY_BYTES = 4
+PASSES = 4
+CPU_SAMPLE_LOG2 = 24          # bounded CPU sample: 2^24 keys of the same workload
+FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag.is_set():
+                    break
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag.set()
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for name, v in zip(names, s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples and self.samples[0][1].isdigit() else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_gkeys(sample_log2, dataset, iterations):
+    """RadixSortCPU<uint32_t>::sort on a 2^sample_log2 prefix of the workload's input, averaged like
+    _NUM_PERFORMANCE_ITERATIONS (src/CRadixSortTask.cpp:203-221).  Single host thread."""
+    import numpy as np
+    from oracle import Oracle, Reference, have_reference
+    n = 1 << sample_log2
+    ora = Oracle()
+    data = ora.dataset(dataset, KEY_TYPE, n, 0x5EED)
+    if have_reference():
+        ref = Reference()
+        ms = ref.time_radix_sort_cpu_ms(data, KEY_TYPE, iterations)
+        kind = "reference"
+    else:
+        t0 = time.perf_counter()
+        for _ in range(iterations):
+            ora.radix_sort_cpu(data, KEY_TYPE)
+        ms = (time.perf_counter() - t0) * 1e3 / iterations
+        kind = "port"
+    return {"value": n / ms / 1e6, "unit": UNIT, "cores": 1, "kind": kind, "host_cores_available": os.cpu_count(),
+            "sample": f"2^{sample_log2} uint32 keys, '{dataset}' dataset (reference generator, seed 0x5EED), "
+                      f"{iterations} iterations averaged, RadixSortCPU<uint32_t>::sort, 1 thread",
+            "ms_per_sort": ms}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path, on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    dataset = args.dataset
+    # warm-up + K timed steps; each step = one bounded-sample sort (2^24 keys takes ~2-3 s)
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_gkeys(20, dataset, 1)
+    res = cpu_reference_gkeys(CPU_SAMPLE_LOG2, dataset, max(1, args.steps))
+    n_total = (1 << LOG2_SINGLE) if args.gpus == 1 else (1 << LOG2_DIST_TOTAL)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_sort"], "higher_is_better": True,
+        "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": workload_name(args.gpus, dataset), "keys_total": n_total,
+                   "note": "CPU reference timed on a bounded sample of the workload: " + res["sample"]},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_name(gpus, dataset):
+    if gpus == 1:
+        return f"2^{LOG2_SINGLE} uint32 keys, keys-only, '{dataset}' dataset, 1xB200 (BASELINE.json configs[1])"
+    return (f"2^{LOG2_DIST_TOTAL} uint32 keys total, keys-only, '{dataset}' dataset generated per shard on the devices, "
+            f"{gpus}xB200: local onesweep + MSD splitter all-reduce + NCCL all-to-all + final local sort "
+            f"(BASELINE.json configs[4])")
+
+
+def bench_single(args):
+    import numpy as np
+    import torch
+    rsb = importlib.import_module("radix-sort_b200")
+    n = 1 << args.log2n
+    torch.cuda.set_device(0)
+    ctx = rsb.Context(0)
+    st = rsb.Stream(ctx, torch.cuda.current_stream().cuda_stream)
+    d_in = torch.empty(n, dtype=torch.int32, device="cuda")
+    bufs = [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(2)]
+    sorter = rsb.Sorter(ctx, KEY_TYPE, n, rsb.RS_NO_KEY_BUFFERS)
+
+    def sort_once():
+        return sorter.sort_device(st, d_in.data_ptr(), bufs[0].data_ptr(), bufs[1].data_ptr(), n)
+
+    datasets = ["uniform", "random", "range", "inverted", "zeros"]
+    per_dataset = {}
+    headline = None
+    clocks = None
+    launches = 0
+    rt_head = None
+    for kind in [args.dataset] + [d for d in datasets if d != args.dataset]:
+        ctx.fill_dataset(st, KEY_TYPE, kind, d_in.data_ptr(), n, seed=0x5EED)
+        for _ in range(max(args.warmup, 3)):
+            r = sort_once()
+        torch.cuda.synchronize()
+        sorter.reset_runtimes()
+        l0 = sorter.launch_count
+        sampler = None
+        if kind == args.dataset:
+            sampler = ClockSampler(0)
+            sampler.start()
+            time.sleep(0.25)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            sort_once()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        if sampler is not None:
+            time.sleep(0.15)
+            clocks = sampler.finish()
+        chk = ctx.check(st, KEY_TYPE, bufs[r].data_ptr(), n)
+        if chk["unordered"] != 0:
+            raise RuntimeError(f"bench: output of dataset {kind} is not sorted")
+        per_dataset[kind] = round(n / ms / 1e6, 3)
+        if kind == args.dataset:
+            headline = ms
+            launches = sorter.launch_count - l0
+            rt_head = sorter.runtimes()
+
+    # ---- end to end through the reference-facing calls with pinned HOST buffers ---------------------------
+    h_in = rsb.HostBuffer(n, np.uint32)
+    h_out = rsb.HostBuffer(n, np.uint32)
+    ctx.fill_dataset(st, KEY_TYPE, args.dataset, d_in.data_ptr(), n, seed=0x5EED)
+    torch.cuda.synchronize()
+    h_in.array[:] = d_in.cpu().numpy().view(np.uint32)   # same workload, now living in pinned host memory
+    e2e_sorter = rsb.Sorter(ctx, KEY_TYPE, n)
+    e2e_steps = max(1, min(args.steps, 5))
+
+    def e2e_once():
+        e2e_sorter.upload(st, h_in, None, n)
+        e2e_sorter.sort(st, n)
+        e2e_sorter.download(st, h_out, None, n)   # blocks: result is in host memory
+
+    e2e_once()
+    e2e_once()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_once()
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    out = h_out.array
+    if not bool((out[1:] >= out[:-1]).all()):
+        raise RuntimeError("bench: e2e output is not sorted")
+    e2e = {"value": n / e2e_ms / 1e6, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "h2d_bytes_per_step": n * KEY_BYTES, "d2h_bytes_per_step": n * KEY_BYTES,
+           "api": "rs_sorter_upload -> rs_sorter_sort -> rs_sorter_download (pinned host buffers)"}
+
+    # ---- roofline of the dominant kernel (one onesweep pass) ----------------------------------------------
+    peak, peak_src = measured_hbm_peak()
+    pass_ms = rt_head["time_reorder"]["avg"] / PASSES
+    alg_bytes = 2 * KEY_BYTES * n
+    achieved = alg_bytes / (pass_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("onesweep_u32_keys_2^28_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "rs_onesweep_kernel<u32, keys-only> (one pass)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": pass_ms,
+                "whole_sort": {"algorithmic_bytes": (KEY_BYTES + PASSES * 2 * KEY_BYTES) * n,
+                               "achieved": (KEY_BYTES + PASSES * 2 * KEY_BYTES) * n / (headline * 1e-3) / 1e9,
+                               "frac": (KEY_BYTES + PASSES * 2 * KEY_BYTES) * n / (headline * 1e-3) / 1e9 / peak},
+                "phases_ms": {"histogram": rt_head["time_histo"]["avg"], "scan": rt_head["time_scan"]["avg"],
+                              "onesweep_passes": rt_head["time_reorder"]["avg"], "total": rt_head["time_total"]["avg"]}}
+    cpu = cpu_reference_gkeys(CPU_SAMPLE_LOG2, args.dataset, 5) if not args.no_cpu else None
+    line = {
+        "metric": METRIC, "value": n / headline / 1e6, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": headline, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": workload_name(1, args.dataset), "keys": n, "passes": PASSES, "digit_bits": 8,
+                   "l2": "inputs (1 GiB per buffer) are larger than the 126 MB L2; no flush needed",
+                   "datasets_gkeys_s": per_dataset},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def bench_distributed(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rsb = importlib.import_module("radix-sort_b200")
+    dsort = importlib.import_module("radix-sort_b200.dist")
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    total = 1 << args.log2n_total
+    n_local = total // world
+    ctx = rsb.Context(local_rank)
+    st = rsb.Stream(ctx, torch.cuda.current_stream().cuda_stream)
+    ops = dsort.CudaOps(rsb, ctx, st, KEY_TYPE, n_local + n_local // 8 + (1 << 20))
+    cap = n_local + n_local // 8 + (1 << 20)
+    shard = ops.empty(n_local)
+    scratch = {k: ops.empty(cap) for k in ("a", "b", "recv", "c")}
+    ctx.fill_dataset(st, KEY_TYPE, args.dataset, shard.data_ptr(), n_local, seed=0x5EED,
+                     global_offset=rank * n_local, total_n=total)
+    before = ctx.check(st, KEY_TYPE, shard.data_ptr(), n_local)
+
+    def step():
+        return dsort.distributed_sort(shard, ops, dist, KEY_TYPE, scratch=scratch)
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    l0 = ops.sorter.launch_count
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = ops.sorter.launch_count - l0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    clocks = sampler.finish() if sampler else None
+
+    # ---- end to end: shard in pinned host memory -> H2D -> distributed sort -> D2H of this rank's result ----
+    h_in = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
+    h_out = torch.empty(cap, dtype=torch.int32, pin_memory=True)
+    h_in.copy_(shard)
+    d_shard = ops.empty(n_local)
+    e2e_steps = max(1, min(args.steps, 2))
+
+    def e2e_once():
+        d_shard.copy_(h_in, non_blocking=True)
+        res = dsort.distributed_sort(d_shard, ops, dist, KEY_TYPE, scratch=scratch)
+        h_out[:res.numel()].copy_(res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return res.numel()
+
+    e2e_once()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        n_out = e2e_once()
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e = {"value": total / e2e_ms / 1e6, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "h2d_bytes_per_step": n_local * KEY_BYTES * world, "d2h_bytes_per_step": int(n_out) * KEY_BYTES * world,
+           "api": "pinned host shard -> H2D -> radix-sort_b200.dist.distributed_sort -> D2H, every rank"}
+    out = dsort.distributed_sort(shard, ops, dist, KEY_TYPE, scratch=scratch)
+    torch.cuda.synchronize()
+
+    # global verification: locally sorted, boundaries ordered across ranks, multiset preserved, exact balance
+    after = ctx.check(st, KEY_TYPE, out.data_ptr(), out.numel())
+    edge = torch.stack([out[0], out[-1]]).to(torch.int64) & 0xFFFFFFFF if out.numel() else torch.zeros(2, dtype=torch.int64, device="cuda")
+    edges = [torch.empty_like(edge) for _ in range(world)]
+    dist.all_gather(edges, edge)
+    fp = torch.tensor([before["sum"] & ((1 << 62) - 1), before["hash_xor"] & ((1 << 62) - 1), after["sum"] & ((1 << 62) - 1),
+                       after["hash_xor"] & ((1 << 62) - 1), after["unordered"], out.numel()], dtype=torch.int64, device="cuda")
+    fps = [torch.empty_like(fp) for _ in range(world)]
+    dist.all_gather(fps, fp)
+    if rank == 0:
+        fps = torch.stack(fps).cpu().numpy().astype(np.uint64)
+        ok = int(fps[:, 4].sum()) == 0 and int(fps[:, 5].sum()) == total
+        mask = np.uint64((1 << 62) - 1)
+        ok = ok and (np.bitwise_xor.reduce(fps[:, 1]) == np.bitwise_xor.reduce(fps[:, 3]))
+        ok = ok and ((fps[:, 0].sum() & mask) == (fps[:, 2].sum() & mask))
+        e = torch.stack(edges).cpu().numpy()
+        ok = ok and all(e[r, 1] <= e[r + 1, 0] for r in range(world - 1))
+        ok = ok and all(int(fps[r, 5]) == ((r + 1) * total) // world - (r * total) // world for r in range(world))
+        if not ok:
+            raise RuntimeError("bench: distributed output failed verification")
+        peak, peak_src = measured_hbm_peak()
+        # per GPU: two local sorts (36 B/key each) over HBM, 4*(P-1)/P B/key out and in over NVLink
+        nvlink_bytes = KEY_BYTES * n_local * (world - 1) / world
+        line = {
+            "metric": METRIC, "value": total / ms_max / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": workload_name(world, args.dataset), "keys_total": total, "keys_per_gpu": n_local,
+                       "l2": "shards are GiBs, far larger than L2"},
+            "clocks": clocks,
+            "e2e": e2e, "gpu_launches": launches * world,
+            "roofline": {"bound": "hbm", "kernel": "whole step per GPU (2 local sorts + exchange)",
+                         "achieved": 2 * (KEY_BYTES + PASSES * 2 * KEY_BYTES) * n_local / (ms_max * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+                         "frac": 2 * (KEY_BYTES + PASSES * 2 * KEY_BYTES) * n_local / (ms_max * 1e-3) / 1e9 / peak,
+                         "traffic": None,
+                         "nvlink": {"bytes_out_per_gpu": nvlink_bytes, "peak_gbs_per_direction": 770.0,
+                                    "min_exchange_ms": nvlink_bytes / 770e9 * 1e3}},
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dataset", default="uniform", choices=["uniform", "random", "range", "inverted", "zeros"])
+    ap.add_argument("--log2n", type=int, default=LOG2_SINGLE, help="single-GPU keys (default 28 = the contract workload)")
+    ap.add_argument("--log2n-total", type=int, default=LOG2_DIST_TOTAL, help="multi-GPU total keys (default 33)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (developer runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 or world > 1:
+        if world == 1:
+            print(json.dumps({"error": "--gpus N>1 must be launched with torch.distributed.run"}))
+            return 2
+        return bench_distributed(args)
+    return bench_single(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

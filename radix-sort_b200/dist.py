@@ -1,0 +1,174 @@
+"""Multi-GPU sort on one NVSwitch box: one process per GPU (torch.distributed), keys-only.
+
+Path (BASELINE.json north_star): every GPU sorts its shard with the local onesweep,
+MSD splitter histograms (16 bits per level) are all-reduced, every rank computes the same exact
+splitters (ties on a splitter value are split by count -- equal keys are indistinguishable), key
+ranges are exchanged with ONE all-to-all-v over NVLink (NCCL), and every GPU sorts what it received.
+Afterwards rank r holds exactly its share of the global order: keys(r) <= keys(r+1), and the
+concatenation over ranks is the sorted input.
+
+The reference has no counterpart (one OpenCL device, Common/ComputeState.cpp:10-12); this is the new
+L2' layer of SURVEY.md section 1.  torch is only plumbing here (device memory, NCCL collectives);
+all sorting and searching on the GPU goes through librsb200.so (`CudaOps`).  The host logic is
+written against the small `ops` interface so it can be exercised on CPU with gloo by the tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+LEVEL_BITS = 16
+
+
+def _key_bits(key_type: str) -> int:
+    return 32 if key_type in ("u32", "i32") else 64
+
+
+def _sign(key_type: str) -> int:
+    return (1 << (_key_bits(key_type) - 1)) if key_type[0] == "i" else 0
+
+
+class CudaOps:
+    """Device operations of the distributed sort, all through the C ABI (no CPU fallback)."""
+
+    def __init__(self, rsb, ctx, stream, key_type: str, max_keys: int):
+        import torch
+        self.torch, self.rsb, self.ctx, self.stream, self.key_type = torch, rsb, ctx, stream, key_type
+        self.tdt = torch.int32 if _key_bits(key_type) == 32 else torch.int64
+        self.sorter = rsb.Sorter(ctx, key_type, max_keys, rsb.RS_NO_KEY_BUFFERS | rsb.RS_NO_PROFILE)
+        self.max_keys = max_keys
+        self._q = None
+        self._pos = None
+
+    def empty(self, n: int):
+        return self.torch.empty(n, dtype=self.tdt, device="cuda")
+
+    def local_sort(self, keys, buf0, buf1):
+        """Sort `keys` (device tensor) using two scratch tensors; returns the tensor holding the result."""
+        n = keys.numel()
+        if n == 0:
+            return buf0[:0]
+        r = self.sorter.sort_device(self.stream, keys.data_ptr(), buf0.data_ptr(), buf1.data_ptr(), n)
+        return (buf0, buf1)[r][:n]
+
+    def lower_bound(self, sorted_keys, queries: np.ndarray) -> np.ndarray:
+        """positions[i] = first index with key >= queries[i] (type-aware); queries are raw key bit patterns."""
+        torch = self.torch
+        nq = len(queries)
+        signed = queries.astype(np.uint64).view(np.int64) if self.tdt == torch.int64 else \
+            queries.astype(np.uint32).view(np.int32)
+        q = torch.from_numpy(np.ascontiguousarray(signed)).to("cuda", non_blocking=False)
+        pos = torch.empty(nq, dtype=torch.int64, device="cuda")
+        torch.cuda.current_stream().synchronize()
+        self.ctx.lower_bound(self.stream, self.key_type, sorted_keys.data_ptr(), sorted_keys.numel(), q.data_ptr(), nq,
+                             pos.data_ptr())
+        self.stream.sync()
+        return pos.cpu().numpy()
+
+    def close(self):
+        self.sorter.close()
+
+
+def plan_exchange(sorted_keys, ops, dist, key_type: str, group=None, device=None):
+    """Exact splitters + per-destination cut positions in this rank's sorted shard.
+
+    Returns (cuts, recv_counts): cuts has world+1 entries (cuts[0]=0, cuts[-1]=n_local); rank d receives
+    sorted_keys[cuts[d]:cuts[d+1]] from this rank.  Rank j ends with the keys whose global (stable) rank
+    lies in [j*N/P, (j+1)*N/P), so shard sizes differ by at most one key whatever the distribution.
+    """
+    import torch
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    bits, sign = _key_bits(key_type), _sign(key_type)
+    top = 1 << bits                      # one past the largest ordered-unsigned key
+    n_local = int(sorted_keys.numel())
+    dev = device if device is not None else sorted_keys.device
+
+    def allreduce_np(a: np.ndarray) -> np.ndarray:
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return t.cpu().numpy()
+
+    def positions(ordered: np.ndarray, is_top: np.ndarray | None = None) -> np.ndarray:
+        """lower bound of ordered-unsigned values (uint64; entries flagged is_top mean `top`) in the local shard"""
+        vals = (ordered & np.uint64(top - 1)) ^ np.uint64(sign)
+        pos = ops.lower_bound(sorted_keys, vals).astype(np.int64)
+        if is_top is not None:
+            pos[is_top] = n_local
+        return pos
+
+    n_total = int(allreduce_np(np.array([n_local]))[0])
+    if world == 1:
+        return np.array([0, n_local], dtype=np.int64), np.array([n_local], dtype=np.int64)
+    targets = [(j * n_total) // world for j in range(1, world)]  # global rank of the first key of rank j
+    prefix = [0] * (world - 1)   # per splitter: ordered-unsigned key bits resolved so far
+    below = [0] * (world - 1)    # per splitter: number of keys globally below `prefix`
+    levels = bits // LEVEL_BITS
+    fan = 1 << LEVEL_BITS
+    for level in range(levels):
+        shift = bits - LEVEL_BITS * (level + 1)
+        bases = [0] if level == 0 else prefix      # level 0: one histogram serves every splitter
+        steps = np.arange(fan + 1, dtype=np.uint64) << np.uint64(shift)   # uint64 wrap-around == mod 2^64
+        q = np.stack([np.uint64(b) + steps for b in bases])
+        is_top = np.zeros(q.shape, dtype=bool)
+        is_top[:, -1] = [b + (fan << shift) >= top for b in bases]         # the last boundary may be `top` itself
+        pos = positions(q.reshape(-1), is_top.reshape(-1)).reshape(q.shape)
+        counts = allreduce_np(np.diff(pos, axis=1))   # [len(bases)][65536] global sub-range counts
+        for j in range(world - 1):
+            c = counts[0 if level == 0 else j]
+            cum = below[j] + np.concatenate(([0], np.cumsum(c)))
+            b = int(np.searchsorted(cum, targets[j], side="right") - 1)  # cum[b] <= target < cum[b+1]
+            b = min(max(b, 0), fan - 1)
+            prefix[j] += b << shift
+            below[j] = int(cum[b])
+    # prefix[j] is now an exact key value v_j; the copies of v_j are split by count, in rank order
+    pairs = [x for j in range(world - 1) for x in (prefix[j], prefix[j] + 1)]
+    pos = positions(np.array([x & 0xFFFFFFFFFFFFFFFF for x in pairs], dtype=np.uint64),
+                    np.array([x >= top for x in pairs], dtype=bool))
+    lb, ub = pos[0::2], pos[1::2]
+    eq_local = ub - lb
+    mine = torch.from_numpy(np.ascontiguousarray(eq_local, dtype=np.int64)).to(dev)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    eq_all = np.stack([p.cpu().numpy() for p in parts])  # [rank][splitter]
+    cuts = np.zeros(world + 1, dtype=np.int64)
+    cuts[-1] = n_local
+    for j in range(world - 1):
+        need_left = targets[j] - below[j]              # copies of v_j that belong to ranks <= j
+        before_me = int(eq_all[:rank, j].sum())
+        share = min(max(need_left - before_me, 0), int(eq_local[j]))
+        cuts[j + 1] = lb[j] + share
+    cuts = np.maximum.accumulate(cuts)  # equal splitters (heavy duplicates) keep the cuts monotone
+    t_send = torch.from_numpy(np.diff(cuts).copy()).to(dev)
+    t_recv = torch.empty_like(t_send)
+    dist.all_to_all_single(t_recv, t_send, group=group)
+    return cuts, t_recv.cpu().numpy()
+
+
+def distributed_sort(keys, ops, dist, key_type: str, scratch=None, group=None):
+    """Sort the union of all ranks' `keys`; returns this rank's slice of the global order (device tensor).
+
+    keys     : this rank's shard (device tensor, int32/int64 storage of the key bit patterns)
+    ops      : CudaOps (product) -- or a test double with local_sort / lower_bound / empty
+    scratch  : optional dict of preallocated tensors {"a","b","recv","c"} (each >= the largest shard) so the
+               timed region does not allocate
+    """
+    n_local = int(keys.numel())
+    s = scratch or {}
+
+    def buf(name, n):
+        t = s.get(name)
+        return t if (t is not None and t.numel() >= n) else ops.empty(n)
+
+    a, b = buf("a", n_local), buf("b", n_local)
+    sorted_local = ops.local_sort(keys, a[:n_local], b[:n_local])
+    cuts, recv_counts = plan_exchange(sorted_local, ops, dist, key_type, group=group)
+    n_recv = int(recv_counts.sum())
+    recv = buf("recv", n_recv)[:n_recv]
+    dist.all_to_all_single(recv, sorted_local, output_split_sizes=[int(c) for c in recv_counts],
+                           input_split_sizes=[int(c) for c in np.diff(cuts)], group=group)
+    # final local sort of the received runs; the buffer the local result does not live in is free again
+    free = a if sorted_local.data_ptr() != a.data_ptr() else b
+    if free.numel() < n_recv:
+        free = ops.empty(n_recv)
+    c = buf("c", n_recv)
+    return ops.local_sort(recv, free[:n_recv], c[:n_recv])
