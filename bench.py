@@ -67,7 +67,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag.is_set():
@@ -175,6 +175,9 @@ def bench_single(args):
     clocks = None
     launches = 0
     rt_head = None
+    sampler = ClockSampler(0)   # samples clocks while all five datasets are sorted (warm-ups + timed steps)
+    sampler.start()
+    time.sleep(0.3)
     for kind in [args.dataset] + [d for d in datasets if d != args.dataset]:
         ctx.fill_dataset(st, KEY_TYPE, kind, d_in.data_ptr(), n, seed=0x5EED)
         for _ in range(max(args.warmup, 3)):
@@ -182,11 +185,6 @@ def bench_single(args):
         torch.cuda.synchronize()
         sorter.reset_runtimes()
         l0 = sorter.launch_count
-        sampler = None
-        if kind == args.dataset:
-            sampler = ClockSampler(0)
-            sampler.start()
-            time.sleep(0.25)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
@@ -195,9 +193,6 @@ def bench_single(args):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
-        if sampler is not None:
-            time.sleep(0.15)
-            clocks = sampler.finish()
         chk = ctx.check(st, KEY_TYPE, bufs[r].data_ptr(), n)
         if chk["unordered"] != 0:
             raise RuntimeError(f"bench: output of dataset {kind} is not sorted")
@@ -206,6 +201,8 @@ def bench_single(args):
             headline = ms
             launches = sorter.launch_count - l0
             rt_head = sorter.runtimes()
+
+    clocks = sampler.finish()
 
     # ---- end to end through the reference-facing calls with pinned HOST buffers ---------------------------
     h_in = rsb.HostBuffer(n, np.uint32)
@@ -325,6 +322,20 @@ def bench_distributed(args):
     clocks = sampler.finish() if sampler else None
 
     # ---- end to end: shard in pinned host memory -> H2D -> distributed sort -> D2H of this rank's result ----
+    def host_mem_available():
+        try:
+            for ln in open("/proc/meminfo"):
+                if ln.startswith("MemAvailable:"):
+                    return int(ln.split()[1]) * 1024
+        except Exception:
+            pass
+        return 0
+
+    need = (n_local + cap) * KEY_BYTES * world          # pinned bytes over all ranks of this box
+    e2e_ok = torch.tensor([1 if host_mem_available() > 3 * need else 0], dtype=torch.int64, device="cuda")
+    dist.all_reduce(e2e_ok, op=dist.ReduceOp.MIN)
+    if int(e2e_ok.item()) == 0:
+        raise RuntimeError("bench: not enough host memory for the pinned end-to-end buffers")
     h_in = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
     h_out = torch.empty(cap, dtype=torch.int32, pin_memory=True)
     h_in.copy_(shard)
@@ -405,7 +416,7 @@ def bench_distributed(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dataset", default="uniform", choices=["uniform", "random", "range", "inverted", "zeros"])
