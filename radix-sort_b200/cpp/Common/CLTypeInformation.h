@@ -1,0 +1,27 @@
+// CLTypeInformation.h -- key-type table (reference Common/CLTypeInformation.h:8-46).  The OpenCL spelling
+// is kept for the CSV "Datatype" column's sibling uses; `key_type` is what the C ABI is told instead of a
+// generated `#define DataType ...` preamble (reference src/RadixSortGPU.cpp:431-442).
+#pragma once
+#include "rsb200.h"
+
+#include <cstdint>
+#include <string_view>
+
+template <typename T>
+struct TypeNameString {};
+
+#define RS_TYPE_ROW(T, CL, HAS_KEY, KEY)                                  \
+    template <>                                                           \
+    struct TypeNameString<T> {                                            \
+        inline static constexpr std::string_view stdint_name  = #T;      \
+        inline static constexpr std::string_view open_cl_name = CL;      \
+        inline static constexpr bool             sortable     = HAS_KEY; \
+        inline static constexpr rs_key_type      key_type     = KEY;     \
+    };
+RS_TYPE_ROW(int16_t, "short", false, RS_KEY_I32)            // named by the reference, not instantiated by its sorter
+RS_TYPE_ROW(uint16_t, "unsigned short", false, RS_KEY_U32)  // (src/RadixSortGPU.cpp:598-601)
+RS_TYPE_ROW(int32_t, "int", true, RS_KEY_I32)
+RS_TYPE_ROW(uint32_t, "unsigned int", true, RS_KEY_U32)
+RS_TYPE_ROW(int64_t, "long", true, RS_KEY_I64)
+RS_TYPE_ROW(uint64_t, "unsigned long", true, RS_KEY_U64)
+#undef RS_TYPE_ROW

@@ -1,0 +1,44 @@
+"""GPU tests of the C++ facade (radix-sort_b200/cpp): the reference's IComputeTask flow and its documented
+library-user sequence, compiled against librsb200.so and run as the reference runs them."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RUNNER = os.path.join(ROOT, "tests", "cpp", "task_runner")
+BASIC = os.path.join(ROOT, "radix-sort_b200", "cpp", "examples", "basic_sort")
+
+
+def _run(cmd):
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+
+
+@pytest.mark.parametrize("n", [1 << 20, 100000, 1024])
+def test_icompute_task_flow_all_types_all_datasets(n):
+    # tests/tests.cpp "Main test": 4 types x 5 datasets through CRadixSortTask (sizes >= 2^10: the envelope in
+    # which the reference's CPU radix sort equals std::sort)
+    out = _run([RUNNER, "--num-elements", str(n), "--perf-csv-to-stdout"])
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert out.stdout.count("GOLD TEST PASSED!") == 20
+    assert out.stdout.count("Validation of CPU RadixSort has passed") == 20
+    assert out.stdout.count("Validation of GPU RadixSort has passed") == 20
+    assert out.stdout.count("Validation of GPU permutation (stable argsort) has passed") == 20
+    assert "INVALID RESULTS!" not in out.stdout and "FAILED" not in out.stdout
+    header = "NumElements,Datatype,Dataset,avgHistogram,avgScan,avgPaste,avgReorder,avgTotalGPU,avgTotalSTLCPU,avgTotalRDXCPU"
+    rows = [l for l in out.stdout.splitlines() if l and l[0].isdigit() and l.count(",") >= 9]
+    assert out.stdout.count(header) == 20 and len(rows) == 20
+    names = {r.split(",")[2] for r in rows}
+    assert names == {"Zeros", "Range", "Inverted Range", "Random Uniform", "Random Random"}
+    assert {r.split(",")[1] for r in rows} == {"uint32_t", "int32_t", "uint64_t", "int64_t"}
+    rounded = (n + 1023) // 1024 * 1024
+    assert all(int(r.split(",")[0]) == rounded for r in rows)
+
+
+def test_basic_sort_example():
+    out = _run([BASIC, str(1 << 20)])
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "Sort verified: results match std::sort" in out.stdout
+    out = _run([BASIC, "77777"])  # ragged: padded tail sorts to the end
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
