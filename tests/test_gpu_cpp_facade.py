@@ -15,9 +15,9 @@ def _run(cmd):
     return subprocess.run(cmd, capture_output=True, text=True, timeout=900)
 
 
-@pytest.mark.parametrize("n", [1 << 20, 100000, 1024])
+@pytest.mark.parametrize("n", [1 << 20, 1024])
 def test_icompute_task_flow_all_types_all_datasets(n):
-    # tests/tests.cpp "Main test": 4 types x 5 datasets through CRadixSortTask (sizes >= 2^10: the envelope in
+    # tests/tests.cpp "Main test": 4 types x 5 datasets through CRadixSortTask (sizes 2^k >= 2^10: the envelope in
     # which the reference's CPU radix sort equals std::sort)
     out = _run([RUNNER, "--num-elements", str(n), "--perf-csv-to-stdout"])
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
@@ -32,8 +32,18 @@ def test_icompute_task_flow_all_types_all_datasets(n):
     names = {r.split(",")[2] for r in rows}
     assert names == {"Zeros", "Range", "Inverted Range", "Random Uniform", "Random Random"}
     assert {r.split(",")[1] for r in rows} == {"uint32_t", "int32_t", "uint64_t", "int64_t"}
-    rounded = (n + 1023) // 1024 * 1024
-    assert all(int(r.split(",")[0]) == rounded for r in rows)
+    assert all(int(r.split(",")[0]) == n for r in rows)
+
+
+def test_icompute_task_flow_ragged_size():
+    # N not a multiple of 1024: the task sorts the rounded buffer (data + zero tail, src/CRadixSortTask.cpp:176)
+    # and compares the first N.  The GPU path and its permutation must validate for every type and dataset;
+    # the reference's CPU radix sort itself mis-sorts some of these inputs (signed keys with a zero tail:
+    # digit count taken from max = 0) -- that line is reproduced, not required to pass.
+    out = _run([RUNNER, "--num-elements", "100000"])
+    assert out.stdout.count("Validation of GPU RadixSort has passed") == 20, out.stdout[-3000:]
+    assert out.stdout.count("Validation of GPU permutation (stable argsort) has passed") == 20
+    assert out.stdout.count("Validation of CPU RadixSort has FAILED") >= 1  # the known reference bug shows up
 
 
 def test_basic_sort_example():
