@@ -22,8 +22,10 @@ static bool sortAndVerify(ComputeState& compute, uint64_t numElements) {
     std::vector<T>        hKeys(rounded), hResult(rounded);
     std::vector<uint32_t> hHistograms(P::_HISTOSIZE), hGlobsum(P::_NUM_HISTOSPLIT), hPermut(rounded);
     std::copy_n(dataset.dataset.begin(), numElements, hKeys.begin());
-    // keys past numElements sort to the end: fill the host tail like padGPUData fills the device tail
-    std::fill(hKeys.begin() + numElements, hKeys.end(), static_cast<T>(std::numeric_limits<T>::max() - 1));
+    // keys past numElements must sort to the end.  The host tail is what uploadData ships (it overwrites the
+    // device-side padGPUData fill, as in the reference), so fill it with max: padGPUData's max-1 would sort
+    // in front of a genuine max key, and RandomDistributed always contains one.
+    std::fill(hKeys.begin() + numElements, hKeys.end(), std::numeric_limits<T>::max());
     std::iota(hPermut.begin(), hPermut.end(), 0U);
     HostSpans<T> spans{{hKeys.data(), hKeys.size()}, {hHistograms.data(), hHistograms.size()},
                        {hGlobsum.data(), hGlobsum.size()}, {hPermut.data(), hPermut.size()},
