@@ -150,9 +150,17 @@ static Plan make_plan(uint64_t n, size_t key_bytes, bool has_vals, int passes) {
 }
 
 template <typename KeyT, int NPASS>
-static cudaError_t launch_hist_n(int grid, cudaStream_t st, const KeyT* keys, uint64_t n, const Plan& pl,
+static cudaError_t launch_hist_n(int grid, cudaStream_t st, const KeyT* keys, uint64_t n, const Plan&,
                                  unsigned long long* hist, const PassTable& pt) {
-    rs_histogram_kernel<KeyT, NPASS><<<grid, HIST_THREADS, 0, st>>>(keys, n, hist, pt);
+    auto kern = rs_histogram_kernel<KeyT, NPASS>;
+    static thread_local bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(HistCfg<NPASS>::bytes));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<grid, HIST_THREADS, HistCfg<NPASS>::bytes, st>>>(keys, n, hist, pt);
     return cudaGetLastError();
 }
 template <typename KeyT>
@@ -160,10 +168,10 @@ static cudaError_t launch_hist(int sm_count, cudaStream_t st, const KeyT* keys, 
                                unsigned long long* hist, const PassTable& pt) {
     const uint64_t vec_per_block = static_cast<uint64_t>(HIST_THREADS) * HIST_VECS * (16 / sizeof(KeyT));
     uint64_t want = (n + vec_per_block - 1) / vec_per_block;
-    // a block's shared-memory counters are 32-bit: keep every block below 2^31 keys
+    // one block per SM (the per-lane tables take most of the shared memory); 32-bit counters: < 2^31 keys per block
     const uint64_t min_grid = (n >> 31) + 1;
     int grid = static_cast<int>(std::max<uint64_t>(
-        min_grid, std::min<uint64_t>(std::max<uint64_t>(want, 1), static_cast<uint64_t>(sm_count) * 4)));
+        min_grid, std::min<uint64_t>(std::max<uint64_t>(want, 1), static_cast<uint64_t>(sm_count))));
     switch (pt.num_passes) {
         case 1: return launch_hist_n<KeyT, 1>(grid, st, keys, n, pl, hist, pt);
         case 2: return launch_hist_n<KeyT, 2>(grid, st, keys, n, pl, hist, pt);

@@ -135,103 +135,85 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Upfront multi-digit histogram.  One coalesced 128-bit read of every key; all `num_passes`
-// digit histograms are accumulated in shared memory and flushed once per (block, chunk).
-// A warp-uniform shortcut keeps degenerate inputs (Zeros, Range, Inverted Range: whole 128-key
-// rows share a digit) from serialising on one shared-memory word: the bits that differ across
-// the row are OR-reduced (REDUX) and a digit whose bits do not differ is counted by one lane.
+// Upfront multi-digit histogram.  One coalesced 128-bit read of every key; all `NPASS` 256-bin
+// histograms are accumulated in shared memory and flushed once per block.
+//
+// ncu on the first version (one table per block, `atomicAdd(&sh[pass][digit])`): LSU data pipe 96 %
+// busy, 68 % of the shared wavefronts were bank conflicts of the random-digit atomics, DRAM at 30 %.
+// So the table is replicated per LANE: sh[pass][digit][col], col = lane % COLS.  With COLS = 32 the
+// bank of an access is the lane, i.e. every ATOMS is one wavefront whatever the digits are -- this
+// also removes the same-address serialisation of degenerate inputs (Zeros, Range) without any
+// warp-uniformity test.  32 KB per pass: one 1024-thread block per SM; for more than 4 passes
+// (64-bit keys) COLS = 16 (two lanes share a column).
 // Algorithmic traffic: sizeof(KeyT) bytes read per key.
 // ------------------------------------------------------------------------------------------------
-constexpr int HIST_THREADS = 512;
+constexpr int HIST_THREADS = 1024;
 constexpr int HIST_VECS    = 4;  // 16-byte vectors in flight per thread
 
-template <typename KeyT, int NPASS>
-__device__ __forceinline__ void hist_accumulate_row(uint32_t* sh, const KeyT (&k)[16 / sizeof(KeyT)], bool active,
-                                                    const PassTable& pt, int lane) {
-    constexpr int KV = 16 / sizeof(KeyT);
-    // bits that differ from lane 0's first key anywhere in this warp row
-    KeyT ref  = k[0];
-    KeyT diff = 0;
-    if constexpr (sizeof(KeyT) == 4) {
-        ref = static_cast<KeyT>(__shfl_sync(0xffffffffu, static_cast<uint32_t>(k[0]), 0));
-    } else {
-        ref = static_cast<KeyT>(__shfl_sync(0xffffffffu, static_cast<unsigned long long>(k[0]), 0));
-    }
-#pragma unroll
-    for (int j = 0; j < KV; ++j) diff |= (k[j] ^ ref);
-    uint32_t dlo = static_cast<uint32_t>(diff);
-    uint32_t dhi = sizeof(KeyT) == 8 ? static_cast<uint32_t>(static_cast<uint64_t>(diff) >> 32) : 0u;
-    const bool all_active = __all_sync(0xffffffffu, active);
-    dlo = __reduce_or_sync(0xffffffffu, dlo);
-    if (sizeof(KeyT) == 8) dhi = __reduce_or_sync(0xffffffffu, dhi);
-    const uint64_t wdiff = (static_cast<uint64_t>(dhi) << 32) | dlo;
-#pragma unroll
-    for (int p = 0; p < NPASS; ++p) {
-        const DigitSpec s = pt.d[p];
-        const bool uniform = all_active && (((wdiff >> s.shift) & s.mask) == 0);
-        if (uniform) {
-            if (lane == 0) atomicAdd(&sh[p * RADIX + digit_of(k[0], s)], 32u * KV);
-        } else if (active) {
-#pragma unroll
-            for (int j = 0; j < KV; ++j) atomicAdd(&sh[p * RADIX + digit_of(k[j], s)], 1u);
-        }
-    }
-}
+template <int NPASS>
+struct HistCfg {
+    static constexpr int    COLS  = NPASS <= 4 ? 32 : 16;
+    static constexpr size_t bytes = sizeof(uint32_t) * NPASS * RADIX * COLS;
+};
 
 template <typename KeyT, int NPASS>
-__global__ void __launch_bounds__(HIST_THREADS)
+__global__ void __launch_bounds__(HIST_THREADS, 1)
 rs_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ hist /* [NPASS][256] */,
                     PassTable pt) {
-    constexpr int KV = 16 / sizeof(KeyT);
-    __shared__ uint32_t sh[NPASS * RADIX];
-    const int  tid     = threadIdx.x;
-    const int  lane    = tid & 31;
-    const bool aligned = (reinterpret_cast<uintptr_t>(keys) & 15u) == 0;
+    constexpr int KV   = 16 / sizeof(KeyT);
+    constexpr int COLS = HistCfg<NPASS>::COLS;
+    extern __shared__ __align__(16) uint32_t hist_sh[];  // [NPASS][256][COLS]
+    const int      tid     = threadIdx.x;
+    const int      lane    = tid & 31;
+    const uint32_t col     = lane & (COLS - 1);
+    const bool     aligned = (reinterpret_cast<uintptr_t>(keys) & 15u) == 0;
 
-    for (int i = tid; i < NPASS * RADIX; i += HIST_THREADS) sh[i] = 0;
+    for (int i = tid; i < NPASS * RADIX * COLS; i += HIST_THREADS) hist_sh[i] = 0;
     __syncthreads();
     const uint64_t nvec = aligned ? n / KV : 0;
     const uint4*   cv   = reinterpret_cast<const uint4*>(keys);
 
-    // whole warps walk the vector range so the warp-uniform shortcut sees full rows; a block never counts
-    // more than 2^32 keys (grid >= n / 2^31 is guaranteed by the launcher)
+    auto count_key = [&](KeyT k) {
+#pragma unroll
+        for (int p = 0; p < NPASS; ++p)
+            atomicAdd(&hist_sh[(p * RADIX + digit_of(k, pt.d[p])) * COLS + col], 1u);
+    };
+
+    // a block never counts more than 2^32 keys per column (the launcher keeps blocks below 2^31 keys)
     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * HIST_THREADS;
     const uint64_t first  = static_cast<uint64_t>(blockIdx.x) * HIST_THREADS + tid;
-    const uint64_t rounds = (nvec + stride * HIST_VECS - 1) / (stride * HIST_VECS);
-    for (uint64_t r = 0; r < rounds; ++r) {
+    for (uint64_t base = first; base < nvec; base += stride * HIST_VECS) {
         uint4 v[HIST_VECS];
         bool  act[HIST_VECS];
 #pragma unroll
         for (int u = 0; u < HIST_VECS; ++u) {
-            const uint64_t idx = first + (r * HIST_VECS + u) * stride;
+            const uint64_t idx = base + u * stride;
             act[u]             = idx < nvec;
             v[u]               = act[u] ? __ldg(cv + idx) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int u = 0; u < HIST_VECS; ++u) {
-            KeyT k[KV];
+            if (!act[u]) continue;
             if constexpr (sizeof(KeyT) == 4) {
-                k[0]      = static_cast<KeyT>(v[u].x);
-                k[1 % KV] = static_cast<KeyT>(v[u].y);
-                k[2 % KV] = static_cast<KeyT>(v[u].z);
-                k[3 % KV] = static_cast<KeyT>(v[u].w);
+                count_key(static_cast<KeyT>(v[u].x));
+                count_key(static_cast<KeyT>(v[u].y));
+                count_key(static_cast<KeyT>(v[u].z));
+                count_key(static_cast<KeyT>(v[u].w));
             } else {
-                k[0]      = static_cast<KeyT>((static_cast<uint64_t>(v[u].y) << 32) | v[u].x);
-                k[1 % KV] = static_cast<KeyT>((static_cast<uint64_t>(v[u].w) << 32) | v[u].z);
+                count_key(static_cast<KeyT>((static_cast<uint64_t>(v[u].y) << 32) | v[u].x));
+                count_key(static_cast<KeyT>((static_cast<uint64_t>(v[u].w) << 32) | v[u].z));
             }
-            hist_accumulate_row<KeyT, NPASS>(sh, k, act[u], pt, lane);
         }
     }
     // scalar tail (and everything when the base pointer is not 16-byte aligned)
-    for (uint64_t i = nvec * KV + first; i < n; i += stride) {
-        const KeyT k = keys[i];
-#pragma unroll
-        for (int p = 0; p < NPASS; ++p) atomicAdd(&sh[p * RADIX + digit_of(k, pt.d[p])], 1u);
-    }
+    for (uint64_t i = nvec * KV + first; i < n; i += stride) count_key(keys[i]);
     __syncthreads();
-    for (int i = tid; i < NPASS * RADIX; i += HIST_THREADS) {
-        const uint32_t v = sh[i];
-        if (v) atomicAdd(&hist[i], static_cast<unsigned long long>(v));
+    // fold the columns (rotated by the lane so a warp's 32 rows hit 32 banks) and flush
+    for (int row = tid; row < NPASS * RADIX; row += HIST_THREADS) {
+        unsigned long long sum = 0;
+#pragma unroll
+        for (int j = 0; j < COLS; ++j) sum += hist_sh[row * COLS + ((j + lane) & (COLS - 1))];
+        if (sum) atomicAdd(&hist[row], sum);
     }
 }
 
