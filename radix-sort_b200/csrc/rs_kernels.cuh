@@ -35,19 +35,6 @@ constexpr int      MAX_PASSES        = 8;
 #define RS_LB_WINDOW 4
 #endif
 constexpr int      LB_WINDOW         = RS_LB_WINDOW;  // look-back status words in flight per thread
-// Ranking primitive (see the measurements quoted above rs_onesweep_kernel):
-//   0 = eight ballots build the match mask (VOTE pipe), one counter update per distinct digit
-//   1 = shared-memory lane bitmap (LSU pipe)
-#ifndef RS_RANK_MODE
-#define RS_RANK_MODE 1
-#endif
-#if RS_RANK_MODE == 0
-using WEntry = uint32_t;                       // [warp][digit] running count
-#define RS_W_CNT(e) (e)
-#else
-using WEntry = uint2;                          // [warp][digit] {lane bitmap, running count}
-#define RS_W_CNT(e) ((e).y)
-#endif
 constexpr unsigned long long BASE_READY = 1ull << 63;      // ready flag of a chunk-base word
 
 struct DigitSpec {
@@ -246,16 +233,22 @@ rs_scan_kernel(const unsigned long long* __restrict__ hist, unsigned long long* 
 // ------------------------------------------------------------------------------------------------
 // Onesweep pass: persistent CTAs take tile ids from an atomic dispenser, prefetch the NEXT tile's
 // keys into shared memory with a 1-D bulk async copy (TMA) while ranking the current one, rank the
-// digits warp by warp, resolve the tile's global digit offsets with a decoupled look-back over
-// status words, stage the keys (and values) in shared memory in ranked order and write them out in
-// coalesced per-digit runs.  Stable.
+// digits half-warp by half-warp, resolve the tile's global digit offsets with a decoupled look-back
+// over status words, stage the keys (and values) in shared memory in ranked order and write them
+// out in coalesced per-digit runs.  Stable.
 //
-// Ranking (measured on B200, tools/ubench.cu): MATCH.ANY costs ~1.4 cycles per DISTINCT value per
-// SM (45 cycles for random 8-bit digits), 8 ballots cost 17; a shared-memory bitmap -- every lane
-// ORs its lane bit into word [warp][digit], reads the word back, the lowest lane of each group
-// clears it and bumps the group's running count -- costs ~4.  Rows whose 32 digits are all equal
-// (Zeros, the high digits of Range) would serialise on one word, so they take a warp-uniform
-// shortcut decided by one MATCH.ALL.
+// Ranking (measured on B200, tools/ubench.cu and ncu): MATCH.ANY costs ~1.4 cycles per DISTINCT
+// value per SM (45 cycles for random 8-bit digits; ADU pipe 78 % busy in the first version), eight
+// ballots cost 17 and share the MIO path with the LSU.  Cheapest is a shared-memory lane bitmap:
+// every lane ORs its lane bit into word [group][digit], reads the word back, the lowest lane of
+// each match group clears the bitmap and bumps the group's running count.  The kernel is bound by
+// shared-memory wavefronts (LSU data pipe ~88 % busy), so the table word is ONE 32-bit word
+// {count:16 | bitmap:16} per (half-warp, digit): three 32-bit accesses per key instead of one
+// 32-bit and two 64-bit ones (the 64-bit layout halves the banks a 32-bit access can use).
+// A half-warp owns 16*KPT consecutive keys of the tile and walks them 16 at a time, so the order of
+// processing is the index order and ranks are stable.  Rows whose 16 digits are all equal (Zeros,
+// the high digits of Range) would serialise on one word, so they take a shortcut decided by one
+// shuffle + vote per row.
 // Algorithmic traffic: sizeof(KeyT) read + sizeof(KeyT) written per key (+4+4 with values).
 // ------------------------------------------------------------------------------------------------
 template <typename KeyT>
@@ -279,14 +272,17 @@ template <typename KeyT, bool HAS_VALS, int THREADS, int KPT>
 struct OnesweepSmem {
     static constexpr int    TILE   = THREADS * KPT;
     static constexpr int    NWARPS = THREADS / 32;
+    static constexpr int    NHALF  = NWARPS * 2;    // half-warp ranking groups
+    static constexpr int    PARTS  = THREADS / RADIX;  // threads per digit in the scan phase
     static constexpr size_t stage_bytes = sizeof(KeyT) * TILE;
     static constexpr size_t off_stage0  = 0;
     static constexpr size_t off_stage1  = off_stage0 + stage_bytes;
     static constexpr size_t off_vstage  = off_stage1 + stage_bytes;
-    static constexpr size_t off_wtab    = off_vstage + (HAS_VALS ? sizeof(uint32_t) * TILE : 0);
-    static constexpr size_t off_kptr    = off_wtab + sizeof(WEntry) * NWARPS * RADIX;
+    static constexpr size_t off_tab     = off_vstage + (HAS_VALS ? sizeof(uint32_t) * TILE : 0);
+    static constexpr size_t off_kptr    = off_tab + sizeof(uint32_t) * NHALF * RADIX;
     static constexpr size_t off_vptr    = off_kptr + sizeof(void*) * RADIX;
-    static constexpr size_t off_wsum    = off_vptr + (HAS_VALS ? sizeof(void*) * RADIX : 0);
+    static constexpr size_t off_ptot    = off_vptr + (HAS_VALS ? sizeof(void*) * RADIX : 0);
+    static constexpr size_t off_wsum    = off_ptot + sizeof(uint32_t) * PARTS * RADIX;
     static constexpr size_t off_mbar    = off_wsum + sizeof(uint32_t) * 16;
     static constexpr size_t off_tile    = off_mbar + sizeof(uint64_t) * 2;
     static constexpr size_t total       = off_tile + sizeof(uint32_t) * 4;
@@ -296,29 +292,38 @@ template <typename KeyT, bool HAS_VALS, int THREADS, int KPT, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
     using L = OnesweepSmem<KeyT, HAS_VALS, THREADS, KPT>;
-    constexpr int TILE   = L::TILE;
-    constexpr int NWARPS = L::NWARPS;
-    static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit needed");
+    constexpr int TILE  = L::TILE;
+    constexpr int NHALF = L::NHALF;
+    constexpr int PARTS = L::PARTS;
+    constexpr int HPP   = NHALF / PARTS;  // half-warp tables per scan thread
+    static_assert(THREADS % RADIX == 0 && NHALF % PARTS == 0, "THREADS must be a multiple of 256");
     static_assert((sizeof(KeyT) * TILE) % 128 == 0, "stage must keep 128B alignment");
+    static_assert(TILE <= 0xffff, "16-bit count / position fields");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     KeyT* const        stage0  = reinterpret_cast<KeyT*>(smem_raw + L::off_stage0);  // stage s = stage0 + s*TILE
     uint32_t* const    vstage  = reinterpret_cast<uint32_t*>(smem_raw + L::off_vstage);
-    WEntry* const      wtab    = reinterpret_cast<WEntry*>(smem_raw + L::off_wtab);  // [warp][digit]
-    KeyT** const       kptr    = reinterpret_cast<KeyT**>(smem_raw + L::off_kptr);   // [digit] -> keys_out run - tile pos
+    uint32_t* const    tab     = reinterpret_cast<uint32_t*>(smem_raw + L::off_tab);   // [half-warp][digit] count<<16 | bitmap
+    KeyT** const       kptr    = reinterpret_cast<KeyT**>(smem_raw + L::off_kptr);     // [digit] -> keys_out run - tile pos
     uint32_t** const   vptr    = reinterpret_cast<uint32_t**>(smem_raw + L::off_vptr);
+    uint32_t* const    ptot    = reinterpret_cast<uint32_t*>(smem_raw + L::off_ptot);  // [part][digit] partial digit totals
     uint32_t* const    wsum    = reinterpret_cast<uint32_t*>(smem_raw + L::off_wsum);
     uint64_t* const    mbar    = reinterpret_cast<uint64_t*>(smem_raw + L::off_mbar);
     volatile uint32_t* sh_tile = reinterpret_cast<volatile uint32_t*>(smem_raw + L::off_tile);
 
-    const int       tid      = threadIdx.x;
-    const int       lane     = tid & 31;
-    const int       warp     = tid >> 5;
-    const uint32_t  lt       = lanemask_lt();
-    const uint32_t  lane_bit = 1u << lane;
-    const DigitSpec ds       = a.digit;
+    const int       tid   = threadIdx.x;
+    const int       lane  = tid & 31;
+    const int       warp  = tid >> 5;
+    const int       l16   = lane & 15;
+    const int       hw    = warp * 2 + (lane >> 4);               // this lane's half-warp
+    const uint32_t  bit16 = 1u << l16;
+    const uint32_t  lt16  = bit16 - 1u;
+    const DigitSpec ds    = a.digit;
     const uint32_t  full_tiles = static_cast<uint32_t>(a.n / TILE);  // tiles [0, full_tiles) are complete
-    WEntry* const   wt       = wtab + warp * RADIX;
+    uint32_t* const ht    = tab + hw * RADIX;
+    // scan-phase role: digit `sd`, half-warp tables [sp*HPP, sp*HPP + HPP)
+    const int       sd    = tid & (RADIX - 1);
+    const int       sp    = tid / RADIX;
 
     auto issue_prefetch = [&](uint32_t t, int s) {
         // thread 0 only: bulk copy of a complete tile into stage s
@@ -338,9 +343,9 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
         sh_tile[0]        = t0;
         if (t0 < a.num_tiles) issue_prefetch(t0, 0);
     }
-    // the warp tables start clean; every tile leaves its bitmaps clear and re-zeroes the counts itself
+    // the tables start clean; every tile re-zeroes them itself after its scatter
 #pragma unroll
-    for (int i = 0; i < RADIX / 32; ++i) wt[lane + 32 * i] = WEntry{};
+    for (int j = 0; j < HPP; ++j) tab[(sp * HPP + j) * RADIX + sd] = 0u;
     __syncthreads();
 
     uint32_t phase_bits = 0;  // bit s = parity to wait for on mbar[s]
@@ -351,7 +356,7 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
         const bool     via_tma  = FULL && a.use_tma;
         const uint64_t tile_base = static_cast<uint64_t>(t) * TILE;
         const uint32_t valid    = FULL ? TILE : static_cast<uint32_t>(a.n - tile_base);
-        const uint32_t my_first = warp * (32 * KPT) + lane;  // warp-striped: item r sits at my_first + 32*r
+        const uint32_t my_first = hw * (16 * KPT) + l16;  // half-warp-striped: item r sits at my_first + 16*r
         KeyT* const    stg      = stage0 + s * TILE;
 
         // ---- keys (and values) into registers -------------------------------------------------
@@ -360,11 +365,11 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
             mbar_wait(&mbar[s], (phase_bits >> s) & 1u);
             phase_bits ^= (1u << s);
 #pragma unroll
-            for (int r = 0; r < KPT; ++r) key[r] = stg[my_first + 32 * r];
+            for (int r = 0; r < KPT; ++r) key[r] = stg[my_first + 16 * r];
         } else {
 #pragma unroll
             for (int r = 0; r < KPT; ++r) {
-                const uint32_t i = my_first + 32 * r;
+                const uint32_t i = my_first + 16 * r;
                 key[r] = (FULL || i < valid) ? a.keys_in[tile_base + i] : static_cast<KeyT>(~static_cast<KeyT>(0));
             }
         }
@@ -372,103 +377,92 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
         if constexpr (HAS_VALS) {
 #pragma unroll
             for (int r = 0; r < KPT; ++r) {
-                const uint32_t i = my_first + 32 * r;
+                const uint32_t i = my_first + 16 * r;
                 val[r]           = (FULL || i < valid) ? a.vals_in[tile_base + i] : 0u;
             }
         }
 
-        // ---- rank within the warp ---------------------------------------------------------------
-        uint32_t rank[KPT];
+        // ---- rank within the half-warp ----------------------------------------------------------
+        uint32_t rk[(KPT + 1) / 2];  // two 16-bit ranks per register (rank < 16*KPT)
 #pragma unroll
         for (int r = 0; r < KPT; ++r) {
             uint32_t d = digit_of(key[r], ds);
-            if (!FULL && (my_first + 32 * r) >= valid) d = RADIX - 1;  // padding ranks last
-            int all_same;
-            __match_all_sync(0xffffffffu, d, &all_same);
-#if RS_RANK_MODE == 0
-            uint32_t m = 0xffffffffu;
-            if (!all_same) {  // warp-uniform branch
-#pragma unroll
-                for (int b = 0; b < RADIX_BITS; ++b) {
-                    const bool     bit = (d >> b) & 1u;
-                    const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-                    m &= bit ? bal : ~bal;
-                }
-            }
-            const uint32_t below  = __popc(m & lt);
-            const int      leader = __ffs(m) - 1;
-            uint32_t       prev   = 0;
-            if (below == 0) prev = atomicAdd(&wt[d], static_cast<uint32_t>(__popc(m)));  // lowest lane of the group
-            prev    = __shfl_sync(0xffffffffu, prev, leader);
-            rank[r] = prev + below;
-#else
-            if (all_same) {  // warp-uniform: 32 equal digits, ranks follow the lane order
-                const uint32_t c = wt[d].y;
+            if (!FULL && (my_first + 16 * r) >= valid) d = RADIX - 1;  // padding ranks last
+            uint32_t my_rank;
+            // warp-uniform test "both half-warps hold 16 equal digits" (all masks stay compile-time constants)
+            const uint32_t d_first = __shfl_sync(0xffffffffu, d, lane & 16);
+            if (__all_sync(0xffffffffu, d == d_first)) {
+                // ranks follow the lane order, one lane per half-warp bumps the count
+                const uint32_t e = ht[d];
                 __syncwarp();
-                if (lane == 0) wt[d].y = c + 32u;
-                rank[r] = c + lane;
+                if (l16 == 0) ht[d] = e + (16u << 16);
+                my_rank = (e >> 16) + l16;
             } else {
-                atomicOr(&wt[d].x, lane_bit);
+                atomicOr(&ht[d], bit16);
                 __syncwarp();
-                const uint2 e = wt[d];
+                const uint32_t e = ht[d];
                 __syncwarp();
-                const uint32_t below = __popc(e.x & lt);
-                if (below == 0) wt[d] = make_uint2(0u, e.y + __popc(e.x));  // lowest lane of the group
-                rank[r] = e.y + below;
+                const uint32_t below = __popc(e & lt16);
+                if (below == 0) ht[d] = (e & 0xffff0000u) + (static_cast<uint32_t>(__popc(e & 0xffffu)) << 16);
+                my_rank = (e >> 16) + below;
             }
-#endif
             __syncwarp();
+            if (r & 1) rk[r >> 1] |= my_rank << 16; else rk[r >> 1] = my_rank;
         }
-        __syncthreads();  // (A) all warp counts final; every key of this stage is in registers
+        __syncthreads();  // (A) all half-warp counts final; every key of this stage is in registers
 
-        // ---- per-digit: scan over warps, publish the tile aggregate, scan over digits ----------
+        // ---- scan: every thread owns digit sd of HPP half-warp tables ----------------------------
         const uint32_t chunk          = t / a.tiles_per_chunk;
         const bool     first_in_chunk = (t % a.tiles_per_chunk) == 0;
-        uint32_t       count = 0, incl = 0;
-        uint32_t*      my_status = a.status + static_cast<size_t>(t) * RADIX + tid;
-        if (tid < RADIX) {
-            uint32_t sum = 0;
+        uint32_t       pre[(HPP + 1) / 2];  // exclusive prefixes over this thread's tables, two 16-bit values per register
+        uint32_t       part_sum = 0;
 #pragma unroll
-            for (int w = 0; w < NWARPS; ++w) {
-                const uint32_t c                 = RS_W_CNT(wtab[w * RADIX + tid]);
-                RS_W_CNT(wtab[w * RADIX + tid]) = sum;
-                sum += c;
-            }
-            count = sum;
-            if (!FULL && tid == RADIX - 1) count -= (TILE - valid);
-            st_status(my_status, (first_in_chunk ? STATUS_INCLUSIVE : STATUS_LOCAL) | count);
-            incl = count;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += x;
-            }
-            if (lane == 31) wsum[warp] = incl;
+        for (int j = 0; j < HPP; ++j) {
+            if (j & 1) pre[j >> 1] |= part_sum << 16; else pre[j >> 1] = part_sum;
+            part_sum += tab[(sp * HPP + j) * RADIX + sd] >> 16;
         }
-        __syncthreads();  // (B)
-        uint32_t local_base = 0;
-        if (tid < RADIX) {
-            uint32_t woff = 0;
+        ptot[sp * RADIX + sd] = part_sum;
+        __syncthreads();  // (B1)
+        uint32_t count = 0, before_part = 0;
 #pragma unroll
-            for (int w = 0; w < RADIX / 32; ++w) woff += (w < warp) ? wsum[w] : 0u;
-            local_base = woff + incl - count;
-#pragma unroll
-            for (int w = 0; w < NWARPS; ++w) RS_W_CNT(wtab[w * RADIX + tid]) += local_base;
+        for (int q = 0; q < PARTS; ++q) {
+            const uint32_t v = ptot[q * RADIX + sd];
+            count += v;
+            before_part += (q < sp) ? v : 0u;
         }
-        __syncthreads();  // (C) wtab[w][d].y = tile-local position of warp w's first key with digit d
+        if (!FULL && sd == RADIX - 1) count -= (TILE - valid);
+        uint32_t* my_status = a.status + static_cast<size_t>(t) * RADIX + sd;
+        if (sp == 0) st_status(my_status, (first_in_chunk ? STATUS_INCLUSIVE : STATUS_LOCAL) | count);
+        uint32_t incl = count;  // inclusive scan over the 256 digits (each part computes it redundantly)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += x;
+        }
+        if (sp == 0 && lane == 31) wsum[warp] = incl;
+        __syncthreads();  // (B2)
+        uint32_t woff = 0;
+#pragma unroll
+        for (int w = 0; w < RADIX / 32; ++w) woff += (w < (sd >> 5)) ? wsum[w] : 0u;
+        const uint32_t local_base = woff + incl - count;  // tile-local start of digit sd
+#pragma unroll
+        for (int j = 0; j < HPP; ++j)
+            tab[(sp * HPP + j) * RADIX + sd] =
+                (local_base + before_part + ((j & 1) ? (pre[j >> 1] >> 16) : (pre[j >> 1] & 0xffffu))) << 16;
+        __syncthreads();  // (C) tab[h][d] >> 16 = tile-local position of half-warp h's first key with digit d
 
         // ---- scatter into shared memory in ranked order -----------------------------------------
 #pragma unroll
         for (int r = 0; r < KPT; ++r) {
             uint32_t d = digit_of(key[r], ds);
-            if (!FULL && (my_first + 32 * r) >= valid) d = RADIX - 1;
-            const uint32_t pos = RS_W_CNT(wt[d]) + rank[r];
+            if (!FULL && (my_first + 16 * r) >= valid) d = RADIX - 1;
+            const uint32_t pos = (ht[d] >> 16) + ((r & 1) ? (rk[r >> 1] >> 16) : (rk[r >> 1] & 0xffffu));
             stg[swz(pos)]      = key[r];
             if constexpr (HAS_VALS) vstage[swz(pos)] = val[r];
         }
 
         // ---- decoupled look-back: exclusive prefix of this tile's digit counts in its chunk ----
-        if (tid < RADIX) {
+        if (sp == 0) {
             unsigned long long excl = 0;
             if (!first_in_chunk) {
                 // walk back over the predecessors of this chunk, LB_WINDOW status words per round trip
@@ -494,7 +488,7 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
                 st_status(my_status, STATUS_INCLUSIVE | static_cast<uint32_t>(excl + count));
             }
             // global offset of this chunk's first key with this digit (ready at once for chunk 0)
-            unsigned long long* cb_ptr = a.base + static_cast<size_t>(chunk) * RADIX + tid;
+            unsigned long long* cb_ptr = a.base + static_cast<size_t>(chunk) * RADIX + sd;
             unsigned long long  cb;
             do { cb = ld_base(cb_ptr); } while (!(cb & BASE_READY));
             cb &= ~BASE_READY;
@@ -503,14 +497,14 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
                 st_base(cb_ptr + RADIX, BASE_READY | (cb + excl + count));
             // run pointer minus the run's tile-local start: element at tile position p goes to kptr[d][p]
             const long long run0 = static_cast<long long>(cb + excl) - static_cast<long long>(local_base);
-            kptr[tid] = a.keys_out + run0;
-            if constexpr (HAS_VALS) vptr[tid] = a.vals_out + run0;
+            kptr[sd] = a.keys_out + run0;
+            if constexpr (HAS_VALS) vptr[sd] = a.vals_out + run0;
         }
-        __syncthreads();  // (D) staged tile + run pointers visible
+        __syncthreads();  // (D) staged tile + run pointers visible; nobody reads the tables any more
 
-        // ---- coalesced per-digit runs out to global memory; re-zero the warp counts -------------
+        // ---- re-zero the tables; coalesced per-digit runs out to global memory -------------------
 #pragma unroll
-        for (int i = 0; i < RADIX / 32; ++i) RS_W_CNT(wt[lane + 32 * i]) = 0u;
+        for (int j = 0; j < HPP; ++j) tab[(sp * HPP + j) * RADIX + sd] = 0u;
 #pragma unroll
         for (int i = 0; i < KPT; ++i) {
             const uint32_t p = i * THREADS + tid;
