@@ -81,6 +81,7 @@ typedef enum rs_dataset_kind {
 #define RS_NO_TMA           0x2u /* force the plain-load tile path (debug / A-B measurements)    */
 #define RS_NO_PROFILE       0x4u /* do not record per-phase CUDA events in rs_sorter_sort        */
 #define RS_NO_KEY_BUFFERS   0x8u /* allocate only scratch; use rs_sorter_sort_device exclusively */
+#define RS_NO_PASS_SKIP     0x10u /* run every pass even when its digit is the same for all keys       */
 
 typedef struct rs_context_s* rs_context;
 typedef struct rs_stream_s*  rs_stream;
@@ -158,6 +159,11 @@ int rs_sorter_sort_device(rs_sorter s, rs_stream st,
                           const void* d_keys_in, void* d_keys_buf0, void* d_keys_buf1,
                           const uint32_t* d_vals_in, uint32_t* d_vals_buf0, uint32_t* d_vals_buf1,
                           uint64_t n, int begin_bit, int end_bit, int* result_index);
+
+/* Number of passes the last sort skipped on the device because their digit was constant over all keys
+ * (a stable pass over a constant digit is the identity: Zeros, the upper half of 64-bit keys holding 32-bit
+ * values).  Throughput of such a sort must be reported against the unskipped byte count and flagged. Blocks. */
+int rs_sorter_last_skipped_passes(rs_sorter s, rs_stream st, int* skipped);
 
 int rs_sorter_runtimes(rs_sorter s, rs_runtimes* out);       /* blocks on pending events */
 int rs_sorter_reset_runtimes(rs_sorter s);

@@ -12,12 +12,13 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 HEADER = os.path.join(ROOT, "include", "rsb200.h")
-_LIB_PATH = os.path.join(HERE, "librsb200.so")
+# RSB200_LIB: developer override to A/B a differently tuned build of the same library (tools/build_variants.sh)
+_LIB_PATH = os.environ.get("RSB200_LIB") or os.path.join(HERE, "librsb200.so")
 
 KEY_TYPES = {"u32": 0, "i32": 1, "u64": 2, "i64": 3}
 _NP = {"u32": np.uint32, "i32": np.int32, "u64": np.uint64, "i64": np.int64}
 DATASET_KINDS = {"zeros": 0, "range": 1, "inverted": 2, "uniform": 3, "random": 4}
-RS_WITH_PERMUTATION, RS_NO_TMA, RS_NO_PROFILE, RS_NO_KEY_BUFFERS = 0x1, 0x2, 0x4, 0x8
+RS_WITH_PERMUTATION, RS_NO_TMA, RS_NO_PROFILE, RS_NO_KEY_BUFFERS, RS_NO_PASS_SKIP = 0x1, 0x2, 0x4, 0x8, 0x10
 
 _lib = None
 
@@ -95,6 +96,7 @@ def load_library():
         "rs_sorter_download_histograms": ([vp, vp, vp, C.c_size_t, C.POINTER(i)], i),
         "rs_sorter_sort_device": ([vp, vp, vp, vp, vp, vp, vp, vp, u64, i, i, C.POINTER(i)], i),
         "rs_sorter_runtimes": ([vp, C.POINTER(_Runtimes)], i),
+        "rs_sorter_last_skipped_passes": ([vp, vp, C.POINTER(i)], i),
         "rs_sorter_reset_runtimes": ([vp], i),
         "rs_sorter_launch_count": ([vp, C.POINTER(u64)], i),
         "rs_dataset_fill_device": ([vp, vp, i, i, u64, u64, u64, vp, u64], i),
@@ -262,6 +264,11 @@ class Sorter:
                                               _addr(d_vin), _addr(d_vbuf0), _addr(d_vbuf1), n, begin_bit, end_bit,
                                               C.byref(idx)))
         return idx.value
+
+    def last_skipped_passes(self, stream) -> int:
+        v = C.c_int(0)
+        _check(self.lib.rs_sorter_last_skipped_passes(self.handle, stream.handle, C.byref(v)))
+        return v.value
 
     def runtimes(self) -> dict:
         rt = _Runtimes()

@@ -73,6 +73,7 @@ struct rs_sorter_s {
     int       last_passes;
     int       last_chunks;
     size_t    last_hist_offset;
+    size_t    last_plan_offset;
     // profiling
     std::vector<EventQuad> free_events;
     std::vector<EventQuad> pending;
@@ -103,7 +104,12 @@ static void stat_reset(rs_statistics& s) {
 // ------------------------------------------------------------------------------------------------
 template <typename KeyT, bool HAS_VALS>
 struct TileCfg;
-template <> struct TileCfg<uint32_t, false> { static constexpr int THREADS = 512, KPT = 16, MINB = 2; };
+#ifndef RS_U32_THREADS
+#define RS_U32_THREADS 512
+#define RS_U32_KPT 16
+#define RS_U32_MINB 2
+#endif
+template <> struct TileCfg<uint32_t, false> { static constexpr int THREADS = RS_U32_THREADS, KPT = RS_U32_KPT, MINB = RS_U32_MINB; };
 template <> struct TileCfg<uint32_t, true>  { static constexpr int THREADS = 512, KPT = 12, MINB = 2; };
 template <> struct TileCfg<uint64_t, false> { static constexpr int THREADS = 512, KPT = 8,  MINB = 2; };
 template <> struct TileCfg<uint64_t, true>  { static constexpr int THREADS = 512, KPT = 8,  MINB = 2; };
@@ -123,7 +129,7 @@ struct Plan {
     int      num_chunks;
     int      passes;
     // scratch layout (bytes)
-    size_t off_hist, off_ctr, off_status, zero_bytes, off_base, total;
+    size_t off_hist, off_ctr, off_plan, off_status, zero_bytes, off_base, total;
 };
 
 static Plan make_plan(uint64_t n, size_t key_bytes, bool has_vals, int passes) {
@@ -142,6 +148,7 @@ static Plan make_plan(uint64_t n, size_t key_bytes, bool has_vals, int passes) {
     size_t o     = 0;
     p.off_hist   = o; o = align(o + sizeof(uint64_t) * passes * RADIX);
     p.off_ctr    = o; o = align(o + sizeof(uint32_t) * MAX_PASSES);
+    p.off_plan   = o; o = align(o + sizeof(SortPlanDev));
     p.off_base   = o; o = align(o + sizeof(uint64_t) * passes * p.num_chunks * RADIX);
     p.off_status = o; o = align(o + sizeof(uint32_t) * RADIX * p.num_tiles * passes);
     p.zero_bytes = o;
@@ -251,11 +258,16 @@ static int sort_typed(rs_sorter s, cudaStream_t st, const KeyT* in, KeyT* buf0, 
     RS_CUDA(launch_hist<KeyT>(s->ctx->sm_count, st, in, n, pl, hist, pt), RS_CALCULATION_FAILED);
     s->launches++;
     if (profile) RS_CUDA(cudaEventRecord(q.e[1], st), RS_CALCULATION_FAILED);
-    rs_scan_kernel<<<pt.num_passes, RADIX, 0, st>>>(hist, base, pl.num_chunks);
+    auto* plan = reinterpret_cast<SortPlanDev*>(s->scratch + pl.off_plan);
+    const int allow_skip = (s->flags & RS_NO_PASS_SKIP) ? 0 : 1;
+    rs_scan_kernel<<<1, RADIX, 0, st>>>(hist, base, pl.num_chunks, pt.num_passes, n, allow_skip,
+                                       static_cast<const void*>(in) == static_cast<const void*>(buf1) ? 1 : 0, plan);
     RS_CUDA(cudaGetLastError(), RS_CALCULATION_FAILED);
     s->launches++;
     if (profile) RS_CUDA(cudaEventRecord(q.e[2], st), RS_CALCULATION_FAILED);
 
+    const bool all_aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(buf0) |
+                               reinterpret_cast<uintptr_t>(buf1)) & 15u) == 0;
     KeyT*     kb[2] = {buf0, buf1};
     uint32_t* vb[2] = {vbuf0, vbuf1};
     for (int p = 0; p < pt.num_passes; ++p) {
@@ -264,6 +276,8 @@ static int sort_typed(rs_sorter s, cudaStream_t st, const KeyT* in, KeyT* buf0, 
         a.keys_out        = kb[p & 1];
         a.vals_in         = has_vals ? ((p == 0) ? vin : vb[(p - 1) & 1]) : nullptr;
         a.vals_out        = has_vals ? vb[p & 1] : nullptr;
+        a.plan            = plan;
+        a.pass            = p;
         a.n               = n;
         a.base            = base + static_cast<size_t>(p) * pl.num_chunks * RADIX;
         a.status          = status + static_cast<size_t>(p) * pl.num_tiles * RADIX;
@@ -272,7 +286,7 @@ static int sort_typed(rs_sorter s, cudaStream_t st, const KeyT* in, KeyT* buf0, 
         a.tiles_per_chunk = pl.tiles_per_chunk;
         a.num_chunks      = static_cast<uint32_t>(pl.num_chunks);
         a.digit           = pt.d[p];
-        a.use_tma = ((s->flags & RS_NO_TMA) == 0) && ((reinterpret_cast<uintptr_t>(a.keys_in) & 15u) == 0);
+        a.use_tma         = ((s->flags & RS_NO_TMA) == 0) && all_aligned;
         cudaError_t e = has_vals ? launch_pass<KeyT, true>(s->ctx, st, a) : launch_pass<KeyT, false>(s->ctx, st, a);
         if (e != cudaSuccess) return fail(RS_CALCULATION_FAILED, "onesweep launch", e);
         s->launches++;
@@ -284,6 +298,7 @@ static int sort_typed(rs_sorter s, cudaStream_t st, const KeyT* in, KeyT* buf0, 
     s->last_passes      = pt.num_passes;
     s->last_chunks      = pl.num_chunks;
     s->last_hist_offset = pl.off_hist;
+    s->last_plan_offset = pl.off_plan;
     if (result_index) *result_index = (pt.num_passes - 1) & 1;
     return RS_OK;
 }
@@ -712,6 +727,19 @@ int rs_sorter_download_histograms(rs_sorter s, rs_stream st, uint64_t* h_hist, s
     RS_CUDA(cudaMemcpyAsync(h_hist, s->scratch + s->last_hist_offset, static_cast<size_t>(P) * RADIX * sizeof(uint64_t),
                             cudaMemcpyDeviceToHost, st->st), RS_DATA_DOWNLOAD_FAILED);
     RS_CUDA(cudaStreamSynchronize(st->st), RS_DATA_DOWNLOAD_FAILED);
+    return RS_OK;
+}
+
+int rs_sorter_last_skipped_passes(rs_sorter s, rs_stream st, int* skipped) {
+    if (!s || !st || !skipped) return fail(RS_DATA_DOWNLOAD_FAILED, "null argument");
+    *skipped = 0;
+    if (s->last_passes == 0) return RS_OK;
+    RS_CUDA(cudaSetDevice(s->ctx->device), RS_DATA_DOWNLOAD_FAILED);
+    SortPlanDev plan{};
+    RS_CUDA(cudaMemcpyAsync(&plan, s->scratch + s->last_plan_offset, sizeof plan, cudaMemcpyDeviceToHost, st->st),
+            RS_DATA_DOWNLOAD_FAILED);
+    RS_CUDA(cudaStreamSynchronize(st->st), RS_DATA_DOWNLOAD_FAILED);
+    *skipped = static_cast<int>(plan.num_skipped);
     return RS_OK;
 }
 

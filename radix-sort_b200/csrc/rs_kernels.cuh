@@ -37,6 +37,18 @@ constexpr int      MAX_PASSES        = 8;
 constexpr int      LB_WINDOW         = RS_LB_WINDOW;  // look-back status words in flight per thread
 constexpr unsigned long long BASE_READY = 1ull << 63;      // ready flag of a chunk-base word
 
+// Per-sort plan written by rs_scan_kernel: a pass whose digit is the same for every key is the identity
+// (stable sort on a constant digit) and is skipped on the device, without a host round trip.  The
+// ping-pong assignment of the buffers stays the static one (pass p: buf[(p-1)&1] -> buf[p&1], pass 0
+// reads the caller's input), so kernels keep compile-time-constant pointers; a skipped pass either does
+// nothing (skipped passes cancel in pairs) or copies its source to its destination to keep the parity.
+enum : uint32_t { PASS_SORT = 0, PASS_COPY = 1, PASS_NOTHING = 2 };
+struct SortPlanDev {
+    uint32_t action[MAX_PASSES];
+    uint32_t num_skipped;   // passes whose digit was constant
+    uint32_t num_copies;    // of those, how many had to copy
+};
+
 struct DigitSpec {
     int      shift;  // first bit of the digit
     uint32_t mask;   // (1<<bits)-1
@@ -205,29 +217,54 @@ rs_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long lon
 }
 
 // ------------------------------------------------------------------------------------------------
-// Digit-offset scan: one block per pass.  base[p][0][d] = READY | #keys with digit < d.
-// Replaces scanhistograms x2 + pastehistograms of the reference for the GLOBAL part; the per-tile
-// part is the look-back inside rs_onesweep_kernel.  Chunks > 0 (inputs past 2^30 keys) get their
-// base from the last tile of the previous chunk; their words stay 0 (= not ready) here.
+// Digit-offset scan + pass plan: ONE block.  For every pass p: base[p][0][d] = READY | #keys with
+// digit < d (chunks > 0 get their base from the last tile of the previous chunk and stay 0 = not
+// ready here), and skip[p] = "one digit holds all n keys".  Thread 0 then assigns the ping-pong
+// buffers to the passes that do run.  Replaces scanhistograms x2 + pastehistograms of the reference
+// for the GLOBAL part; the per-tile part is the look-back inside rs_onesweep_kernel.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RADIX)
-rs_scan_kernel(const unsigned long long* __restrict__ hist, unsigned long long* __restrict__ base, int num_chunks) {
+rs_scan_kernel(const unsigned long long* __restrict__ hist, unsigned long long* __restrict__ base, int num_chunks,
+               int num_passes, unsigned long long n, int allow_skip, int input_is_buf1, SortPlanDev* __restrict__ plan) {
     __shared__ unsigned long long wsum[RADIX / 32];
-    const int p    = blockIdx.x;
+    __shared__ uint32_t           skip_sh[MAX_PASSES];
     const int d    = threadIdx.x;
     const int lane = d & 31, warp = d >> 5;
-    const unsigned long long total = hist[static_cast<size_t>(p) * RADIX + d];
-    unsigned long long       incl  = total;
+    for (int p = 0; p < num_passes; ++p) {
+        const unsigned long long total = hist[static_cast<size_t>(p) * RADIX + d];
+        unsigned long long       incl  = total;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        const int constant_digit = __syncthreads_or(total == n);  // also orders the wsum writes
+        unsigned long long woff = 0;
+        for (int w = 0; w < warp; ++w) woff += wsum[w];
+        base[static_cast<size_t>(p) * num_chunks * RADIX + d] = BASE_READY | (woff + incl - total);
+        if (d == 0) skip_sh[p] = (allow_skip && constant_digit) ? 1u : 0u;
+        __syncthreads();
     }
-    if (lane == 31) wsum[warp] = incl;
-    __syncthreads();
-    unsigned long long woff = 0;
-    for (int w = 0; w < warp; ++w) woff += wsum[w];
-    base[static_cast<size_t>(p) * num_chunks * RADIX + d] = BASE_READY | (woff + incl - total);
+    if (d == 0) {
+        // Runs of skipped passes cancel in pairs: after (p, p+1) the data is where pass p+2 expects it.  Pass 0 is
+        // special unless the caller's input IS buf1 (the double-buffer call): its source is a third buffer.
+        uint32_t skipped = 0, copies = 0;
+        int p = 0;
+        while (p < num_passes) {
+            if (!skip_sh[p]) { plan->action[p] = PASS_SORT; ++p; continue; }
+            int run_end = p;
+            while (run_end < num_passes && skip_sh[run_end]) ++run_end;
+            skipped += static_cast<uint32_t>(run_end - p);
+            if (p == 0 && !input_is_buf1) { plan->action[0] = PASS_COPY; ++copies; ++p; }
+            const int len = run_end - p;
+            for (int j = 0; j < len; ++j) plan->action[p + j] = PASS_NOTHING;
+            if (len & 1) { plan->action[run_end - 1] = PASS_COPY; ++copies; }
+            p = run_end;
+        }
+        plan->num_skipped = skipped;
+        plan->num_copies  = copies;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -257,6 +294,8 @@ struct OnesweepArgs {
     KeyT*                     keys_out;
     const uint32_t*           vals_in;
     uint32_t*                 vals_out;
+    const SortPlanDev*        plan;
+    int                       pass;
     uint64_t                  n;
     unsigned long long*       base;    // [chunks][256] for this pass: READY | offset (chunks > 0 zeroed)
     uint32_t*                 status;  // [tiles][256] for this pass, zeroed
@@ -311,6 +350,22 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
     uint64_t* const    mbar    = reinterpret_cast<uint64_t*>(smem_raw + L::off_mbar);
     volatile uint32_t* sh_tile = reinterpret_cast<volatile uint32_t*>(smem_raw + L::off_tile);
 
+    {   // constant digit: the pass is the identity -- nothing to do, or a plain copy to keep the ping-pong parity
+        const uint32_t action = a.plan->action[a.pass];
+        if (action == PASS_NOTHING) return;
+        if (action == PASS_COPY) {
+            const uint64_t gtid = blockIdx.x * static_cast<uint64_t>(THREADS) + threadIdx.x;
+            const uint64_t gstr = static_cast<uint64_t>(gridDim.x) * THREADS;
+            constexpr int  KV   = 16 / sizeof(KeyT);
+            const uint64_t nvec = a.use_tma ? a.n / KV : 0;  // use_tma == every key pointer is 16-byte aligned
+            for (uint64_t i = gtid; i < nvec; i += gstr)
+                reinterpret_cast<uint4*>(a.keys_out)[i] = __ldg(reinterpret_cast<const uint4*>(a.keys_in) + i);
+            for (uint64_t i = nvec * KV + gtid; i < a.n; i += gstr) a.keys_out[i] = a.keys_in[i];
+            if constexpr (HAS_VALS)
+                for (uint64_t i = gtid; i < a.n; i += gstr) a.vals_out[i] = a.vals_in[i];
+            return;
+        }
+    }
     const int       tid   = threadIdx.x;
     const int       lane  = tid & 31;
     const int       warp  = tid >> 5;

@@ -152,6 +152,45 @@ def test_pad_value_is_max_minus_one(rsb, gpu):
     assert (out[:1000] == 0).all() and (out[1000:] == np.iinfo(np.int64).max - 1).all()
 
 
+def test_constant_digit_passes_are_skipped_on_device(rsb, gpu, oracle):
+    ctx, st = gpu
+    rng = np.random.default_rng(7)
+    n = 300001
+    cases = {
+        # name: (key type, data, passes expected to be skipped)
+        "zeros": ("u32", np.zeros(n, dtype=np.uint32), 4),
+        "u64 holding 32-bit values (Random<uint64_t>)": ("u64", oracle.dataset("random", "u64", n), 4),
+        "constant byte 1 (odd number of passes runs -> fix-up copy)":
+            ("u32", (rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32) & np.uint32(0xFFFF00FF)) | np.uint32(0x5500), 1),
+        "only byte 2 varies (one pass runs)": ("i32", (rng.integers(0, 256, size=n).astype(np.int32) << 16) | np.int32(0x01000203), 3),
+        "negative constant high bytes": ("i64", -(rng.integers(1, 2**20, size=n).astype(np.int64)), 5),
+    }
+    for name, (t, data, want_skipped) in cases.items():
+        for flags in (0, rsb.RS_NO_PASS_SKIP):
+            s = rsb.Sorter(ctx, t, n, flags | rsb.RS_WITH_PERMUTATION)
+            s.upload(st, data, None, n)
+            s.sort(st, n)
+            out = np.empty(n, dtype=data.dtype)
+            perm = np.empty(n, dtype=np.uint32)
+            s.download(st, out, perm, n)
+            skipped = s.last_skipped_passes(st)
+            s.close()
+            assert np.array_equal(out, np.sort(data)), name
+            assert np.array_equal(perm, np.argsort(data, kind="stable").astype(np.uint32)), name
+            assert skipped == (0 if flags else want_skipped), (name, skipped)
+    # device-pointer entry with a separate input buffer: the input is never written, the result is where promised
+    torch = _torch()
+    data = cases["constant byte 1 (odd number of passes runs -> fix-up copy)"][1]
+    d_in = _dev(data)
+    bufs = [torch.empty_like(d_in), torch.empty_like(d_in)]
+    s = rsb.Sorter(ctx, "u32", n, rsb.RS_NO_KEY_BUFFERS)
+    torch.cuda.synchronize()
+    r = s.sort_device(st, d_in.data_ptr(), bufs[0].data_ptr(), bufs[1].data_ptr(), n)
+    st.sync()
+    assert np.array_equal(_host(bufs[r], np.uint32), np.sort(data)) and np.array_equal(_host(d_in, np.uint32), data)
+    s.close()
+
+
 # ---- device-pointer entry (torch tensors are only the memory plumbing) -----------------------------
 
 def _torch():
