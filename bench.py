@@ -150,7 +150,7 @@ def workload_name(gpus, dataset):
     if gpus == 1:
         return f"2^{LOG2_SINGLE} uint32 keys, keys-only, '{dataset}' dataset, 1xB200 (BASELINE.json configs[1])"
     return (f"2^{LOG2_DIST_TOTAL} uint32 keys total, keys-only, '{dataset}' dataset generated per shard on the devices, "
-            f"{gpus}xB200: local onesweep + MSD splitter all-reduce + NCCL all-to-all + final local sort "
+            f"{gpus}xB200: local onesweep + MSD splitter all-reduce + exchange over NVLink + final local sort "
             f"(BASELINE.json configs[4])")
 
 
@@ -291,8 +291,10 @@ def bench_distributed(args):
     st = rsb.Stream(ctx, torch.cuda.current_stream().cuda_stream)
     ops = dsort.CudaOps(rsb, ctx, st, KEY_TYPE, n_local + n_local // 8 + (1 << 20))
     cap = n_local + n_local // 8 + (1 << 20)
+    if args.exchange == "p2p":
+        ops.enable_p2p(dist, cap)   # fused NVLink pull + histogram kernel instead of NCCL all-to-all
     shard = ops.empty(n_local)
-    scratch = {k: ops.empty(cap) for k in ("a", "b", "recv", "c")}
+    scratch = {k: ops.empty(cap) for k in (("recv", "c") if args.exchange == "p2p" else ("a", "b", "recv", "c"))}
     ctx.fill_dataset(st, KEY_TYPE, args.dataset, shard.data_ptr(), n_local, seed=0x5EED,
                      global_offset=rank * n_local, total_n=total)
     before = ctx.check(st, KEY_TYPE, shard.data_ptr(), n_local)
@@ -400,6 +402,8 @@ def bench_distributed(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(world, args.dataset), "keys_total": total, "keys_per_gpu": n_local,
+                       "exchange": ("fused peer-memory pull + histogram kernel (CUDA IPC over NVLink)" if args.exchange == "p2p"
+                                    else "NCCL all_to_all_single"),
                        "l2": "shards are GiBs, far larger than L2"},
             "clocks": clocks,
             "e2e": e2e, "gpu_launches": launches * world,
@@ -427,6 +431,8 @@ def main():
     ap.add_argument("--log2n", type=int, default=LOG2_SINGLE, help="single-GPU keys (default 28 = the contract workload)")
     ap.add_argument("--log2n-total", type=int, default=LOG2_DIST_TOTAL, help="multi-GPU total keys (default 33)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (developer runs)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU exchange: p2p = fused peer-memory pull + histogram kernel (default), nccl = all_to_all_single")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

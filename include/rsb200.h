@@ -170,6 +170,24 @@ int rs_sorter_reset_runtimes(rs_sorter s);
 /* number of kernels launched by this sorter so far (for the bench's gpu_launches claim) */
 int rs_sorter_launch_count(rs_sorter s, uint64_t* out);
 
+/* ---- multi-GPU building blocks (one process per GPU; the collectives themselves are the caller's) ----------
+ * The reference has no counterpart (single OpenCL device, Common/ComputeState.cpp:10-12). */
+int rs_device_alloc(rs_context ctx, size_t bytes, void** out);      /* plain cudaMalloc: exportable through CUDA IPC */
+int rs_device_free(rs_context ctx, void* p);
+#define RS_IPC_HANDLE_BYTES 64
+int rs_ipc_export(rs_context ctx, const void* d_ptr, unsigned char handle[RS_IPC_HANDLE_BYTES]);  /* d_ptr: base of an rs_device_alloc */
+int rs_ipc_open(rs_context ctx, const unsigned char handle[RS_IPC_HANDLE_BYTES], void** out);     /* map a peer GPU's allocation */
+int rs_ipc_close(rs_context ctx, void* p);
+/* Fused exchange + sort: the input is the concatenation of num_segments (<= 16) device segments that may live in
+ * peer memory (rs_ipc_open).  ONE kernel pulls them over NVLink into d_gathered while it builds the digit histograms
+ * of the sort (visiting the segments round-robin from first_segment); the passes then run as in
+ * rs_sorter_sort_device with d_gathered as the input (it may alias d_keys_buf1).  The caller guarantees that the
+ * peers' segments are complete (a collective after the peers' local sorts) and stay untouched until this call's
+ * gather kernel has run on every rank (a collective after it).  Keys only. */
+int rs_sorter_sort_segments_device(rs_sorter s, rs_stream st, int num_segments, const void* const* d_seg_ptrs,
+                                   const uint64_t* seg_counts, int first_segment, void* d_gathered, void* d_keys_buf0,
+                                   void* d_keys_buf1, int begin_bit, int end_bit, int* result_index);
+
 /* ---- device-side helpers used by the harness and the multi-GPU path ----------------------- */
 /* Fill d_out[0..n) with elements [global_offset, global_offset+n) of a dataset of total_n
  * elements (src/Dataset.h:84-137; the random kinds use a documented counter-based hash). */

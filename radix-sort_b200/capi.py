@@ -99,6 +99,12 @@ def load_library():
         "rs_sorter_last_skipped_passes": ([vp, vp, C.POINTER(i)], i),
         "rs_sorter_reset_runtimes": ([vp], i),
         "rs_sorter_launch_count": ([vp, C.POINTER(u64)], i),
+        "rs_device_alloc": ([vp, C.c_size_t, C.POINTER(vp)], i),
+        "rs_device_free": ([vp, vp], i),
+        "rs_ipc_export": ([vp, vp, C.c_char_p], i),
+        "rs_ipc_open": ([vp, C.c_char_p, C.POINTER(vp)], i),
+        "rs_ipc_close": ([vp, vp], i),
+        "rs_sorter_sort_segments_device": ([vp, vp, i, C.POINTER(vp), C.POINTER(u64), i, vp, vp, vp, i, i, C.POINTER(i)], i),
         "rs_dataset_fill_device": ([vp, vp, i, i, u64, u64, u64, vp, u64], i),
         "rs_check_device": ([vp, vp, i, vp, u64, C.POINTER(u64 * 4)], i),
         "rs_check_permutation_device": ([vp, vp, i, vp, vp, vp, u64, C.POINTER(u64 * 2)], i),
@@ -160,6 +166,28 @@ class Context:
         if self.handle:
             self.lib.rs_context_destroy(self.handle)
             self.handle = C.c_void_p()
+
+    # -- multi-GPU building blocks ---------------------------------------------------------------
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        _check(self.lib.rs_device_alloc(self.handle, nbytes, C.byref(p)))
+        return p.value
+
+    def device_free(self, ptr: int):
+        _check(self.lib.rs_device_free(self.handle, C.c_void_p(ptr)))
+
+    def ipc_export(self, ptr: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(self.lib.rs_ipc_export(self.handle, C.c_void_p(ptr), buf))
+        return buf.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        _check(self.lib.rs_ipc_open(self.handle, C.create_string_buffer(handle, 64), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr: int):
+        _check(self.lib.rs_ipc_close(self.handle, C.c_void_p(ptr)))
 
     # -- device helpers -------------------------------------------------------------------------
     def fill_dataset(self, stream, key_type, kind, d_out, n, seed=0x5EED, global_offset=0, total_n=None):
@@ -269,6 +297,20 @@ class Sorter:
         v = C.c_int(0)
         _check(self.lib.rs_sorter_last_skipped_passes(self.handle, stream.handle, C.byref(v)))
         return v.value
+
+    def sort_segments_device(self, stream, seg_ptrs, seg_counts, first_segment, d_gathered, d_buf0, d_buf1,
+                             begin_bit=0, end_bit=None) -> int:
+        """Fused exchange + sort: pull the (possibly peer-memory) segments into d_gathered while histogramming, then
+        sort; returns the index (0/1) of the buffer that holds the result (buf1 may alias d_gathered)."""
+        end_bit = self.dtype.itemsize * 8 if end_bit is None else end_bit
+        k = len(seg_ptrs)
+        ptrs = (C.c_void_p * k)(*[C.c_void_p(int(p)) for p in seg_ptrs])
+        cnts = (C.c_uint64 * k)(*[int(c) for c in seg_counts])
+        idx = C.c_int(0)
+        _check(self.lib.rs_sorter_sort_segments_device(self.handle, stream.handle, k, ptrs, cnts, first_segment,
+                                                       _addr(d_gathered), _addr(d_buf0), _addr(d_buf1), begin_bit, end_bit,
+                                                       C.byref(idx)))
+        return idx.value
 
     def runtimes(self) -> dict:
         rt = _Runtimes()

@@ -192,6 +192,38 @@ static cudaError_t launch_hist(int sm_count, cudaStream_t st, const KeyT* keys, 
     return cudaErrorInvalidValue;
 }
 
+template <typename KeyT, int NPASS>
+static cudaError_t launch_gather_hist_n(int grid, cudaStream_t st, const SegmentTable<KeyT>& seg, KeyT* gathered,
+                                        unsigned long long* hist, const PassTable& pt) {
+    auto kern = rs_gather_histogram_kernel<KeyT, NPASS>;
+    static thread_local bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(HistCfg<NPASS>::bytes));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<grid, HIST_THREADS, HistCfg<NPASS>::bytes, st>>>(seg, gathered, hist, pt);
+    return cudaGetLastError();
+}
+template <typename KeyT>
+static cudaError_t launch_gather_hist(int sm_count, cudaStream_t st, const SegmentTable<KeyT>& seg, KeyT* gathered,
+                                      uint64_t n, unsigned long long* hist, const PassTable& pt) {
+    const uint64_t min_grid = (n >> 31) + 1;  // 32-bit shared counters: < 2^31 keys per block
+    const int grid = static_cast<int>(std::max<uint64_t>(min_grid, static_cast<uint64_t>(sm_count)));
+    switch (pt.num_passes) {
+        case 1: return launch_gather_hist_n<KeyT, 1>(grid, st, seg, gathered, hist, pt);
+        case 2: return launch_gather_hist_n<KeyT, 2>(grid, st, seg, gathered, hist, pt);
+        case 3: return launch_gather_hist_n<KeyT, 3>(grid, st, seg, gathered, hist, pt);
+        case 4: return launch_gather_hist_n<KeyT, 4>(grid, st, seg, gathered, hist, pt);
+        case 5: return launch_gather_hist_n<KeyT, 5>(grid, st, seg, gathered, hist, pt);
+        case 6: return launch_gather_hist_n<KeyT, 6>(grid, st, seg, gathered, hist, pt);
+        case 7: return launch_gather_hist_n<KeyT, 7>(grid, st, seg, gathered, hist, pt);
+        case 8: return launch_gather_hist_n<KeyT, 8>(grid, st, seg, gathered, hist, pt);
+    }
+    return cudaErrorInvalidValue;
+}
+
 template <typename KeyT, bool HAS_VALS>
 static cudaError_t launch_pass(rs_context ctx, cudaStream_t st, const OnesweepArgs<KeyT>& args) {
     using C = TileCfg<KeyT, HAS_VALS>;
@@ -231,7 +263,7 @@ static PassTable make_pass_table(size_t key_bytes, bool is_signed, int begin_bit
 template <typename KeyT>
 static int sort_typed(rs_sorter s, cudaStream_t st, const KeyT* in, KeyT* buf0, KeyT* buf1, const uint32_t* vin,
                       uint32_t* vbuf0, uint32_t* vbuf1, uint64_t n, int begin_bit, int end_bit, bool profile,
-                      int* result_index) {
+                      int* result_index, const SegmentTable<KeyT>* segments = nullptr) {
     const bool has_vals = vin != nullptr;
     const PassTable pt = make_pass_table(sizeof(KeyT), s->is_signed, begin_bit, end_bit);
     if (pt.num_passes < 1) return fail(RS_CALCULATION_FAILED, "empty bit range");
@@ -255,7 +287,10 @@ static int sort_typed(rs_sorter s, cudaStream_t st, const KeyT* in, KeyT* buf0, 
     auto* base   = reinterpret_cast<unsigned long long*>(s->scratch + pl.off_base);
 
     RS_CUDA(cudaMemsetAsync(s->scratch, 0, pl.zero_bytes, st), RS_CALCULATION_FAILED);
-    RS_CUDA(launch_hist<KeyT>(s->ctx->sm_count, st, in, n, pl, hist, pt), RS_CALCULATION_FAILED);
+    if (segments)  // multi-GPU: pull the peer segments into `in` and count them in the same kernel
+        RS_CUDA(launch_gather_hist<KeyT>(s->ctx->sm_count, st, *segments, const_cast<KeyT*>(in), n, hist, pt), RS_CALCULATION_FAILED);
+    else
+        RS_CUDA(launch_hist<KeyT>(s->ctx->sm_count, st, in, n, pl, hist, pt), RS_CALCULATION_FAILED);
     s->launches++;
     if (profile) RS_CUDA(cudaEventRecord(q.e[1], st), RS_CALCULATION_FAILED);
     auto* plan = reinterpret_cast<SortPlanDev*>(s->scratch + pl.off_plan);
@@ -447,6 +482,26 @@ __global__ void rs_lower_bound_kernel(const U* keys, uint64_t n, const U* q, uin
 static int grid_for(uint64_t n, int threads, int sm_count) {
     uint64_t g = (n + threads - 1) / threads;
     return static_cast<int>(std::max<uint64_t>(1, std::min<uint64_t>(g, static_cast<uint64_t>(sm_count) * 16)));
+}
+
+template <typename KeyT>
+static int sort_segments_typed(rs_sorter s, rs_stream st, int num_segments, const void* const* ptrs, const uint64_t* counts,
+                               int first_segment, void* gathered, void* buf0, void* buf1, int begin_bit, int end_bit,
+                               bool profile, int* result_index) {
+    SegmentTable<KeyT> seg{};
+    seg.num_segments  = num_segments;
+    seg.first_segment = first_segment;
+    uint64_t n = 0;
+    for (int i = 0; i < num_segments; ++i) {
+        seg.ptr[i]   = static_cast<const KeyT*>(ptrs[i]);
+        seg.start[i] = n;
+        n += counts[i];
+    }
+    for (int i = num_segments; i <= MAX_SEGMENTS; ++i) seg.start[i] = n;
+    if (n > s->max_keys) return fail(RS_CALCULATION_FAILED, "segments exceed the sorter's max_keys");
+    if (n == 0) return RS_OK;
+    return sort_typed<KeyT>(s, st->st, static_cast<const KeyT*>(gathered), static_cast<KeyT*>(buf0), static_cast<KeyT*>(buf1),
+                            nullptr, nullptr, nullptr, n, begin_bit, end_bit, profile, result_index, &seg);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -681,6 +736,71 @@ int rs_sorter_sort_device(rs_sorter s, rs_stream st, const void* d_keys_in, void
     return sort_typed<uint64_t>(s, st->st, static_cast<const uint64_t*>(d_keys_in), static_cast<uint64_t*>(d_keys_buf0),
                                 static_cast<uint64_t*>(d_keys_buf1), d_vals_in, d_vals_buf0, d_vals_buf1, n, begin_bit,
                                 end_bit, profile, result_index);
+}
+
+int rs_sorter_sort_segments_device(rs_sorter s, rs_stream st, int num_segments, const void* const* d_seg_ptrs,
+                                   const uint64_t* seg_counts, int first_segment, void* d_gathered, void* d_keys_buf0,
+                                   void* d_keys_buf1, int begin_bit, int end_bit, int* result_index) {
+    if (!s || !st || !d_seg_ptrs || !seg_counts) return fail(RS_CALCULATION_FAILED, "null argument");
+    if (num_segments < 1 || num_segments > MAX_SEGMENTS) return fail(RS_CALCULATION_FAILED, "1..16 segments supported");
+    if (first_segment < 0 || first_segment >= num_segments) return fail(RS_CALCULATION_FAILED, "bad first_segment");
+    const int key_bits = static_cast<int>(s->key_bytes) * 8;
+    if (begin_bit < 0 || end_bit > key_bits || begin_bit >= end_bit) return fail(RS_CALCULATION_FAILED, "bad bit range");
+    const int passes = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
+    if (result_index) *result_index = (passes - 1) & 1;
+    if (!d_gathered || !d_keys_buf0 || (passes > 1 && !d_keys_buf1)) return fail(RS_CALCULATION_FAILED, "null key buffer");
+    if (d_gathered == d_keys_buf0) return fail(RS_CALCULATION_FAILED, "gathered must not alias buf0");
+    RS_CUDA(cudaSetDevice(s->ctx->device), RS_CALCULATION_FAILED);
+    const bool profile = (s->flags & RS_NO_PROFILE) == 0;
+    if (profile) {
+        int rc = resolve_pending(s, false);
+        if (rc != RS_OK) return rc;
+    }
+    if (s->key_bytes == 4)
+        return sort_segments_typed<uint32_t>(s, st, num_segments, d_seg_ptrs, seg_counts, first_segment, d_gathered,
+                                             d_keys_buf0, d_keys_buf1, begin_bit, end_bit, profile, result_index);
+    return sort_segments_typed<uint64_t>(s, st, num_segments, d_seg_ptrs, seg_counts, first_segment, d_gathered,
+                                         d_keys_buf0, d_keys_buf1, begin_bit, end_bit, profile, result_index);
+}
+
+int rs_device_alloc(rs_context ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return fail(RS_INITIALIZATION_FAILED, "null argument");
+    *out = nullptr;
+    RS_CUDA(cudaSetDevice(ctx->device), RS_INITIALIZATION_FAILED);
+    RS_CUDA(cudaMalloc(out, bytes ? bytes : 1), RS_INITIALIZATION_FAILED);
+    return RS_OK;
+}
+int rs_device_free(rs_context ctx, void* p) {
+    if (!ctx) return fail(RS_CLEANUP_FAILED, "null argument");
+    if (!p) return RS_OK;
+    RS_CUDA(cudaSetDevice(ctx->device), RS_CLEANUP_FAILED);
+    RS_CUDA(cudaFree(p), RS_CLEANUP_FAILED);
+    return RS_OK;
+}
+int rs_ipc_export(rs_context ctx, const void* d_ptr, unsigned char handle[RS_IPC_HANDLE_BYTES]) {
+    if (!ctx || !d_ptr || !handle) return fail(RS_INITIALIZATION_FAILED, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == RS_IPC_HANDLE_BYTES, "IPC handle size");
+    RS_CUDA(cudaSetDevice(ctx->device), RS_INITIALIZATION_FAILED);
+    cudaIpcMemHandle_t h;
+    RS_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)), RS_INITIALIZATION_FAILED);
+    memcpy(handle, &h, sizeof h);
+    return RS_OK;
+}
+int rs_ipc_open(rs_context ctx, const unsigned char handle[RS_IPC_HANDLE_BYTES], void** out) {
+    if (!ctx || !handle || !out) return fail(RS_INITIALIZATION_FAILED, "null argument");
+    *out = nullptr;
+    RS_CUDA(cudaSetDevice(ctx->device), RS_INITIALIZATION_FAILED);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    RS_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess), RS_INITIALIZATION_FAILED);
+    return RS_OK;
+}
+int rs_ipc_close(rs_context ctx, void* p) {
+    if (!ctx) return fail(RS_CLEANUP_FAILED, "null argument");
+    if (!p) return RS_OK;
+    RS_CUDA(cudaSetDevice(ctx->device), RS_CLEANUP_FAILED);
+    RS_CUDA(cudaIpcCloseMemHandle(p), RS_CLEANUP_FAILED);
+    return RS_OK;
 }
 
 int rs_sorter_sort(rs_sorter s, rs_stream st, uint64_t n) {

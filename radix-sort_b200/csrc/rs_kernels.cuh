@@ -217,6 +217,79 @@ rs_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long lon
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused exchange + histogram (multi-GPU): the input of a sort is the concatenation of up to
+// MAX_SEGMENTS device segments that may live in PEER memory (other GPUs of the NVSwitch box, mapped
+// through CUDA IPC).  One kernel pulls every segment over NVLink with plain coalesced loads, writes it
+// into the local `gathered` buffer and accumulates the digit histograms of the coming sort on the fly:
+// the all-to-all and the histogram pass of the final local sort are one kernel, the received keys are
+// never re-read for counting.  Segments are visited starting at `first_segment` (= this rank), so at
+// any time every source GPU is read by one reader.  Same per-lane shared-memory tables as above.
+// ------------------------------------------------------------------------------------------------
+constexpr int MAX_SEGMENTS = 16;
+constexpr int GATHER_UNROLL = 8;
+
+template <typename KeyT>
+struct SegmentTable {
+    int                num_segments;
+    int                first_segment;
+    const KeyT*        ptr[MAX_SEGMENTS];
+    unsigned long long start[MAX_SEGMENTS + 1];  // prefix of the segment lengths = position in `gathered`
+};
+
+template <typename KeyT, int NPASS>
+__global__ void __launch_bounds__(HIST_THREADS, 1)
+rs_gather_histogram_kernel(const SegmentTable<KeyT> seg, KeyT* __restrict__ gathered,
+                           unsigned long long* __restrict__ hist /* [NPASS][256] */, PassTable pt) {
+    constexpr int COLS = HistCfg<NPASS>::COLS;
+    extern __shared__ __align__(16) uint32_t hist_sh[];  // [NPASS][256][COLS]
+    const int      tid  = threadIdx.x;
+    const int      lane = tid & 31;
+    const uint32_t col  = lane & (COLS - 1);
+    for (int i = tid; i < NPASS * RADIX * COLS; i += HIST_THREADS) hist_sh[i] = 0;
+    __syncthreads();
+
+    const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * HIST_THREADS;
+    const unsigned long long first  = static_cast<unsigned long long>(blockIdx.x) * HIST_THREADS + tid;
+    for (int k = 0; k < seg.num_segments; ++k) {
+        int sidx = seg.first_segment + k;
+        if (sidx >= seg.num_segments) sidx -= seg.num_segments;
+        // select without dynamic indexing of the by-value table (keeps it in the constant bank)
+        const KeyT*        src = nullptr;
+        unsigned long long beg = 0, end = 0;
+#pragma unroll
+        for (int j = 0; j < MAX_SEGMENTS; ++j)
+            if (j == sidx) { src = seg.ptr[j]; beg = seg.start[j]; end = seg.start[j + 1]; }
+        const unsigned long long cnt = end - beg;
+        KeyT* const              dst = gathered + beg;
+        for (unsigned long long base = first; base < cnt; base += stride * GATHER_UNROLL) {
+            KeyT v[GATHER_UNROLL];
+#pragma unroll
+            for (int u = 0; u < GATHER_UNROLL; ++u) {
+                const unsigned long long i = base + u * stride;
+                if (i < cnt) v[u] = src[i];  // NVLink (or local) read
+            }
+#pragma unroll
+            for (int u = 0; u < GATHER_UNROLL; ++u) {
+                const unsigned long long i = base + u * stride;
+                if (i < cnt) {
+                    dst[i] = v[u];
+#pragma unroll
+                    for (int p = 0; p < NPASS; ++p)
+                        atomicAdd(&hist_sh[(p * RADIX + digit_of(v[u], pt.d[p])) * COLS + col], 1u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int row = tid; row < NPASS * RADIX; row += HIST_THREADS) {
+        unsigned long long sum = 0;
+#pragma unroll
+        for (int j = 0; j < COLS; ++j) sum += hist_sh[row * COLS + ((j + lane) & (COLS - 1))];
+        if (sum) atomicAdd(&hist[row], sum);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Digit-offset scan + pass plan: ONE block.  For every pass p: base[p][0][d] = READY | #keys with
 // digit < d (chunks > 0 get their base from the last tile of the previous chunk and stay 0 = not
 // ready here), and skip[p] = "one digit holds all n keys".  Thread 0 then assigns the ping-pong

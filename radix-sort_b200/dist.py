@@ -64,8 +64,55 @@ class CudaOps:
         self.stream.sync()
         return pos.cpu().numpy()
 
+    # ---- peer-memory exchange (NVLink, CUDA IPC) ---------------------------------------------------------
+    def enable_p2p(self, dist, capacity_keys: int, group=None):
+        """Allocate the two local-sort buffers with plain cudaMalloc, export them through CUDA IPC and map every
+        peer's pair.  After this, distributed_sort replaces the NCCL all-to-all + histogram pass of the final
+        sort by ONE kernel that pulls the peers' segments over NVLink while histogramming them."""
+        torch = self.torch
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        kb = 4 if self.tdt == torch.int32 else 8
+        self.p2p_capacity = capacity_keys
+        self.p2p_local = [self.ctx.device_alloc(capacity_keys * kb) for _ in range(2)]
+        mine = torch.tensor(list(b"".join(self.ctx.ipc_export(p) for p in self.p2p_local)), dtype=torch.uint8, device="cuda")
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        self.p2p_peer = []
+        for r in range(world):
+            if r == rank:
+                self.p2p_peer.append(list(self.p2p_local))
+            else:
+                raw = bytes(parts[r].cpu().tolist())
+                self.p2p_peer.append([self.ctx.ipc_open(raw[0:64]), self.ctx.ipc_open(raw[64:128])])
+        self.p2p_rank, self.p2p_world = rank, world
+        return self
+
+    def p2p_enabled(self) -> bool:
+        return getattr(self, "p2p_peer", None) is not None
+
     def close(self):
+        if self.p2p_enabled():
+            for r, pair in enumerate(self.p2p_peer):
+                if r != self.p2p_rank:
+                    for p in pair:
+                        self.ctx.ipc_close(p)
+            for p in self.p2p_local:
+                self.ctx.device_free(p)
+            self.p2p_peer = None
         self.sorter.close()
+
+
+class RawBuf:
+    """A device range known by address (cudaMalloc'd exchange buffers are not torch tensors)."""
+
+    def __init__(self, ptr: int, n: int, device=None):
+        self._ptr, self._n, self.device = ptr, n, device
+
+    def data_ptr(self) -> int:
+        return self._ptr
+
+    def numel(self) -> int:
+        return self._n
 
 
 def plan_exchange(sorted_keys, ops, dist, key_type: str, group=None, device=None):
@@ -154,6 +201,8 @@ def distributed_sort(keys, ops, dist, key_type: str, scratch=None, group=None):
     """
     n_local = int(keys.numel())
     s = scratch or {}
+    if getattr(ops, "p2p_enabled", None) and ops.p2p_enabled():
+        return _distributed_sort_p2p(keys, ops, dist, key_type, s, group)
 
     def buf(name, n):
         t = s.get(name)
@@ -172,3 +221,46 @@ def distributed_sort(keys, ops, dist, key_type: str, scratch=None, group=None):
         free = ops.empty(n_recv)
     c = buf("c", n_recv)
     return ops.local_sort(recv, free[:n_recv], c[:n_recv])
+
+
+def _distributed_sort_p2p(keys, ops, dist, key_type: str, s, group):
+    """Same result as the NCCL path; the exchange is the fused gather + histogram kernel over peer memory."""
+    import torch
+    world, rank = ops.p2p_world, ops.p2p_rank
+    n_local = int(keys.numel())
+    if n_local > ops.p2p_capacity:
+        raise ValueError("shard larger than the peer-exchange buffers")
+    kb = 4 if _key_bits(key_type) == 32 else 8
+    # 1. local sort into the IPC-exported pair; `sel` says which of the two holds the sorted shard
+    sel = ops.sorter.sort_device(ops.stream, keys.data_ptr(), ops.p2p_local[0], ops.p2p_local[1], n_local) if n_local else 0
+    sorted_local = RawBuf(ops.p2p_local[sel], n_local, device=keys.device)
+    # 2. exact splitters (all-reduces inside: every peer's local sort is complete once they return)
+    cuts, _ = plan_exchange(sorted_local, ops, dist, key_type, group=group, device=keys.device)
+    # 3. everybody learns everybody's cut positions and buffer selector
+    mine = torch.from_numpy(np.concatenate((cuts, [sel])).astype(np.int64)).to(keys.device)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    table = np.stack([p.cpu().numpy() for p in parts])  # [source][world+1 cuts, sel]
+    ptrs, counts = [], []
+    for src in range(world):
+        lo, hi = int(table[src, rank]), int(table[src, rank + 1])
+        ptrs.append(ops.p2p_peer[src][int(table[src, world + 1])] + lo * kb)
+        counts.append(hi - lo)
+    n_recv = int(sum(counts))
+
+    def buf(name, n):
+        t = s.get(name)
+        return t if (t is not None and t.numel() >= n) else ops.empty(max(n, 1))
+
+    gathered, other = buf("recv", n_recv), buf("c", n_recv)
+    # 4. fused exchange + final sort: pull my segments from every peer over NVLink while counting digits
+    if n_recv:
+        r = ops.sorter.sort_segments_device(ops.stream, ptrs, counts, rank, gathered.data_ptr(), other.data_ptr(),
+                                            gathered.data_ptr())
+        out = (other, gathered)[r][:n_recv]
+    else:
+        out = gathered[:0]
+    # 5. nobody may overwrite its sorted shard (next local sort) before every rank has pulled from it
+    done = torch.zeros(1, dtype=torch.int32, device=keys.device)
+    dist.all_reduce(done, group=group)
+    return out

@@ -311,6 +311,35 @@ def test_check_kernels_detect_errors(rsb, gpu, oracle):
     assert np.array_equal(out.cpu().numpy(), np.searchsorted(data, q, side="left"))
 
 
+@pytest.mark.parametrize("t", ("u32", "i64"))
+def test_fused_gather_sort_of_segments(rsb, gpu, oracle, t):
+    # the multi-GPU exchange kernel with all segments local: ragged, unaligned, empty segments; every rotation
+    torch = _torch()
+    ctx, st = gpu
+    data = oracle.dataset("uniform", t, 400000, SEED)
+    d = _dev(data)
+    kb = data.itemsize
+    bounds = [0, 1, 1, 70001, 70004, 250000, 399999, 400000]  # 7 segments, one empty, odd offsets
+    ptrs = [d.data_ptr() + kb * bounds[i] for i in range(len(bounds) - 1)]
+    cnts = [bounds[i + 1] - bounds[i] for i in range(len(bounds) - 1)]
+    n = sum(cnts)
+    g, b0 = torch.empty_like(d), torch.empty_like(d)
+    s = rsb.Sorter(ctx, t, n, rsb.RS_NO_KEY_BUFFERS)
+    torch.cuda.synchronize()
+    for first in range(len(ptrs)):
+        r = s.sort_segments_device(st, ptrs, cnts, first, g.data_ptr(), b0.data_ptr(), g.data_ptr())
+        st.sync()
+        out = _host((b0, g)[r], data.dtype)[:n]
+        assert np.array_equal(out, np.sort(data)), (t, first)
+    # a permuted segment order sorts to the same result and the source is never written
+    order = [3, 0, 6, 5, 1, 4, 2]
+    r = s.sort_segments_device(st, [ptrs[i] for i in order], [cnts[i] for i in order], 2, g.data_ptr(), b0.data_ptr(), g.data_ptr())
+    st.sync()
+    assert np.array_equal(_host((b0, g)[r], data.dtype)[:n], np.sort(data))
+    assert np.array_equal(_host(d, data.dtype), data)
+    s.close()
+
+
 # ---- BASELINE.json full sizes: size-independent properties, everything resident on the device -------
 
 def _full_size_case(rsb, gpu, t, kind, n, with_perm):

@@ -24,10 +24,13 @@ def main():
     ctx = rsb.Context(local_rank)
     st = rsb.Stream(ctx, torch.cuda.current_stream().cuda_stream)
     failures = 0
+    mode = args.get("exchange", "p2p")  # p2p = fused NVLink pull + histogram kernel, nccl = all_to_all_single
     for key_type in ("u32", "i32", "u64", "i64"):
         np_dt = rsb.key_dtype(key_type)
         n_local = total // world + (17 * rank if key_type == "i32" else 0)  # ragged shards for one type
         ops = dsort.CudaOps(rsb, ctx, st, key_type, 2 * n_local + 4096)
+        if mode == "p2p":
+            ops.enable_p2p(dist, 2 * n_local + 4096)
         for kind in ("uniform", "random", "range", "inverted", "zeros"):
             shard = ops.empty(n_local)
             ctx.fill_dataset(st, key_type, kind, shard.data_ptr(), n_local, seed=0x5EED, global_offset=rank * (total // world),
@@ -50,7 +53,7 @@ def main():
                 n_all = len(ins)
                 ok = np.array_equal(outs, np.sort(ins))
                 bal = all(int(sizes[r, 1]) == ((r + 1) * n_all) // world - (r * n_all) // world for r in range(world))
-                print(f"{key_type} {kind:9s} total={n_all} world={world}: {'OK' if ok and bal else 'FAIL'} sizes={sizes[:, 1].tolist()}",
+                print(f"[{mode}] {key_type} {kind:9s} total={n_all} world={world}: {'OK' if ok and bal else 'FAIL'} sizes={sizes[:, 1].tolist()}",
                       flush=True)
                 failures += int(not (ok and bal))
         ops.close()
