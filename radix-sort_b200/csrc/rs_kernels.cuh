@@ -32,7 +32,7 @@ constexpr uint32_t STATUS_VALUE_MASK = (1u << 30) - 1u;
 constexpr uint64_t CHUNK_MAX_KEYS    = (1ull << 30) - 1ull;  // a look-back chain never sums past this
 constexpr int      MAX_PASSES        = 8;
 #ifndef RS_LB_WINDOW
-#define RS_LB_WINDOW 4
+#define RS_LB_WINDOW 8
 #endif
 constexpr int      LB_WINDOW         = RS_LB_WINDOW;  // look-back status words in flight per thread
 constexpr unsigned long long BASE_READY = 1ull << 63;      // ready flag of a chunk-base word
