@@ -82,6 +82,7 @@ typedef enum rs_dataset_kind {
 #define RS_NO_PROFILE       0x4u /* do not record per-phase CUDA events in rs_sorter_sort        */
 #define RS_NO_KEY_BUFFERS   0x8u /* allocate only scratch; use rs_sorter_sort_device exclusively */
 #define RS_NO_PASS_SKIP     0x10u /* run every pass even when its digit is the same for all keys       */
+#define RS_NO_ATOMIC_RANK   0x20u /* rank with the shared-memory lane bitmap even if the atomic mode is available */
 
 typedef struct rs_context_s* rs_context;
 typedef struct rs_stream_s*  rs_stream;
@@ -113,6 +114,9 @@ int rs_device_count(int* n);
 int rs_context_create(int device, rs_context* out);
 int rs_context_destroy(rs_context ctx);
 int rs_context_sm_count(rs_context ctx, int* n);
+/* 1 if the device passed the self-test that allows ranking with one shared atomic per key (see rs_kernels.cuh);
+ * sorters then use that mode unless RS_NO_ATOMIC_RANK is given (env RSB200_NO_ATOMIC_RANK=1 disables it globally). */
+int rs_context_atomic_rank(rs_context ctx, int* enabled);
 int rs_stream_create(rs_context ctx, rs_stream* out);
 /* Wrap an existing cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); not owned. */
 int rs_stream_wrap(rs_context ctx, void* cuda_stream, rs_stream* out);

@@ -18,7 +18,7 @@ _LIB_PATH = os.environ.get("RSB200_LIB") or os.path.join(HERE, "librsb200.so")
 KEY_TYPES = {"u32": 0, "i32": 1, "u64": 2, "i64": 3}
 _NP = {"u32": np.uint32, "i32": np.int32, "u64": np.uint64, "i64": np.int64}
 DATASET_KINDS = {"zeros": 0, "range": 1, "inverted": 2, "uniform": 3, "random": 4}
-RS_WITH_PERMUTATION, RS_NO_TMA, RS_NO_PROFILE, RS_NO_KEY_BUFFERS, RS_NO_PASS_SKIP = 0x1, 0x2, 0x4, 0x8, 0x10
+RS_WITH_PERMUTATION, RS_NO_TMA, RS_NO_PROFILE, RS_NO_KEY_BUFFERS, RS_NO_PASS_SKIP, RS_NO_ATOMIC_RANK = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 
 _lib = None
 
@@ -80,6 +80,7 @@ def load_library():
         "rs_context_create": ([i, C.POINTER(vp)], i),
         "rs_context_destroy": ([vp], i),
         "rs_context_sm_count": ([vp, C.POINTER(i)], i),
+        "rs_context_atomic_rank": ([vp, C.POINTER(i)], i),
         "rs_stream_create": ([vp, C.POINTER(vp)], i),
         "rs_stream_wrap": ([vp, vp, C.POINTER(vp)], i),
         "rs_stream_sync": ([vp], i),
@@ -161,6 +162,12 @@ class Context:
         n = C.c_int(0)
         _check(self.lib.rs_context_sm_count(self.handle, C.byref(n)))
         return n.value
+
+    @property
+    def atomic_rank(self) -> bool:
+        n = C.c_int(0)
+        _check(self.lib.rs_context_atomic_rank(self.handle, C.byref(n)))
+        return bool(n.value)
 
     def close(self):
         if self.handle:

@@ -43,6 +43,7 @@ struct rs_context_s {
     int device;
     int sm_count;
     int max_smem_optin;
+    int atomic_rank_ok;  // the device passed rs_atomic_order_selftest_kernel (same-word shared atomics in lane order)
 };
 struct rs_stream_s {
     rs_context   ctx;
@@ -62,6 +63,7 @@ struct rs_sorter_s {
     size_t      key_bytes;
     bool        is_signed;
     bool        has_vals;
+    bool        atomic_rank;  // ranking mode of the onesweep kernel (see rs_kernels.cuh)
     // device memory
     void*     keys[2];
     uint32_t* vals[2];
@@ -102,24 +104,38 @@ static void stat_reset(rs_statistics& s) {
 // ------------------------------------------------------------------------------------------------
 // tile configurations (per key width / payload) and launch plumbing
 // ------------------------------------------------------------------------------------------------
-template <typename KeyT, bool HAS_VALS>
+// THREADS x KPT keys per tile, MINB CTAs per SM.  Measured on B200 with tools/build_variants.sh.
+template <typename KeyT, bool HAS_VALS, bool ATOMIC>
 struct TileCfg;
 #ifndef RS_U32_THREADS
-// measured on B200 (tools/build_variants.sh): 256 x 24 with 3 CTAs/SM beats 512 x 16 x 2 by 3 % (uniform) to 7 % (range)
 #define RS_U32_THREADS 256
 #define RS_U32_KPT 24
 #define RS_U32_MINB 3
 #endif
-template <> struct TileCfg<uint32_t, false> { static constexpr int THREADS = RS_U32_THREADS, KPT = RS_U32_KPT, MINB = RS_U32_MINB; };
-template <> struct TileCfg<uint32_t, true>  { static constexpr int THREADS = 512, KPT = 12, MINB = 2; };
-template <> struct TileCfg<uint64_t, false> { static constexpr int THREADS = 512, KPT = 8,  MINB = 2; };
-template <> struct TileCfg<uint64_t, true>  { static constexpr int THREADS = 512, KPT = 8,  MINB = 2; };
+#ifndef RS_U32A_THREADS
+#define RS_U32A_THREADS 256
+#define RS_U32A_KPT 24
+#define RS_U32A_MINB 3
+#endif
+template <> struct TileCfg<uint32_t, false, false> { static constexpr int THREADS = RS_U32_THREADS, KPT = RS_U32_KPT, MINB = RS_U32_MINB; };
+template <> struct TileCfg<uint32_t, true,  false> { static constexpr int THREADS = 512, KPT = 12, MINB = 2; };
+template <> struct TileCfg<uint64_t, false, false> { static constexpr int THREADS = 512, KPT = 8,  MINB = 2; };
+template <> struct TileCfg<uint64_t, true,  false> { static constexpr int THREADS = 512, KPT = 8,  MINB = 2; };
+template <> struct TileCfg<uint32_t, false, true>  { static constexpr int THREADS = RS_U32A_THREADS, KPT = RS_U32A_KPT, MINB = RS_U32A_MINB; };
+template <> struct TileCfg<uint32_t, true,  true>  { static constexpr int THREADS = 512, KPT = 12, MINB = 2; };
+template <> struct TileCfg<uint64_t, false, true>  { static constexpr int THREADS = 512, KPT = 8,  MINB = 2; };
+template <> struct TileCfg<uint64_t, true,  true>  { static constexpr int THREADS = 512, KPT = 8,  MINB = 2; };
 
-static int tile_keys(size_t key_bytes, bool has_vals) {
-    if (key_bytes == 4) return has_vals ? TileCfg<uint32_t, true>::THREADS * TileCfg<uint32_t, true>::KPT
-                                        : TileCfg<uint32_t, false>::THREADS * TileCfg<uint32_t, false>::KPT;
-    return has_vals ? TileCfg<uint64_t, true>::THREADS * TileCfg<uint64_t, true>::KPT
-                    : TileCfg<uint64_t, false>::THREADS * TileCfg<uint64_t, false>::KPT;
+template <typename KeyT, bool HAS_VALS, bool ATOMIC>
+static constexpr int tile_of() { return TileCfg<KeyT, HAS_VALS, ATOMIC>::THREADS * TileCfg<KeyT, HAS_VALS, ATOMIC>::KPT; }
+
+static int tile_keys(size_t key_bytes, bool has_vals, bool atomic) {
+    if (key_bytes == 4) {
+        if (atomic) return has_vals ? tile_of<uint32_t, true, true>() : tile_of<uint32_t, false, true>();
+        return has_vals ? tile_of<uint32_t, true, false>() : tile_of<uint32_t, false, false>();
+    }
+    if (atomic) return has_vals ? tile_of<uint64_t, true, true>() : tile_of<uint64_t, false, true>();
+    return has_vals ? tile_of<uint64_t, true, false>() : tile_of<uint64_t, false, false>();
 }
 
 struct Plan {
@@ -133,9 +149,9 @@ struct Plan {
     size_t off_hist, off_ctr, off_plan, off_status, zero_bytes, off_base, total;
 };
 
-static Plan make_plan(uint64_t n, size_t key_bytes, bool has_vals, int passes) {
+static Plan make_plan(uint64_t n, size_t key_bytes, bool has_vals, bool atomic, int passes) {
     Plan p{};
-    p.tile            = tile_keys(key_bytes, has_vals);
+    p.tile            = tile_keys(key_bytes, has_vals, atomic);
     p.num_tiles       = (n + p.tile - 1) / p.tile;
     p.tiles_per_chunk = static_cast<uint32_t>(CHUNK_MAX_KEYS / p.tile);
     // test hook: shrink the look-back chunk so the multi-chunk path can be checked exactly at small n
@@ -225,11 +241,11 @@ static cudaError_t launch_gather_hist(int sm_count, cudaStream_t st, const Segme
     return cudaErrorInvalidValue;
 }
 
-template <typename KeyT, bool HAS_VALS>
-static cudaError_t launch_pass(rs_context ctx, cudaStream_t st, const OnesweepArgs<KeyT>& args) {
-    using C = TileCfg<KeyT, HAS_VALS>;
-    using L = OnesweepSmem<KeyT, HAS_VALS, C::THREADS, C::KPT>;
-    auto kern = rs_onesweep_kernel<KeyT, HAS_VALS, C::THREADS, C::KPT, C::MINB>;
+template <typename KeyT, bool HAS_VALS, bool ATOMIC>
+static cudaError_t launch_pass_mode(rs_context ctx, cudaStream_t st, const OnesweepArgs<KeyT>& args) {
+    using C = TileCfg<KeyT, HAS_VALS, ATOMIC>;
+    using L = OnesweepSmem<KeyT, HAS_VALS, C::THREADS, C::KPT, ATOMIC>;
+    auto kern = rs_onesweep_kernel<KeyT, HAS_VALS, C::THREADS, C::KPT, C::MINB, ATOMIC>;
     static thread_local int cached_device = -1;
     static thread_local int blocks_per_sm = 0;
     if (cached_device != ctx->device) {
@@ -244,6 +260,10 @@ static cudaError_t launch_pass(rs_context ctx, cudaStream_t st, const OnesweepAr
     const int grid = static_cast<int>(std::min<uint64_t>(args.num_tiles, resident));
     kern<<<grid, C::THREADS, L::total, st>>>(args);
     return cudaGetLastError();
+}
+template <typename KeyT, bool HAS_VALS>
+static cudaError_t launch_pass(rs_context ctx, cudaStream_t st, const OnesweepArgs<KeyT>& args, bool atomic) {
+    return atomic ? launch_pass_mode<KeyT, HAS_VALS, true>(ctx, st, args) : launch_pass_mode<KeyT, HAS_VALS, false>(ctx, st, args);
 }
 
 static PassTable make_pass_table(size_t key_bytes, bool is_signed, int begin_bit, int end_bit) {
@@ -268,7 +288,7 @@ static int sort_typed(rs_sorter s, cudaStream_t st, const KeyT* in, KeyT* buf0, 
     const bool has_vals = vin != nullptr;
     const PassTable pt = make_pass_table(sizeof(KeyT), s->is_signed, begin_bit, end_bit);
     if (pt.num_passes < 1) return fail(RS_CALCULATION_FAILED, "empty bit range");
-    const Plan pl = make_plan(n, sizeof(KeyT), has_vals, pt.num_passes);
+    const Plan pl = make_plan(n, sizeof(KeyT), has_vals, s->atomic_rank, pt.num_passes);
     if (pl.total > s->scratch_bytes) return fail(RS_CALCULATION_FAILED, "n exceeds the sorter's max_keys (scratch too small)");
     if (pl.num_tiles >= (1ull << 32)) return fail(RS_CALCULATION_FAILED, "too many tiles");
 
@@ -323,7 +343,8 @@ static int sort_typed(rs_sorter s, cudaStream_t st, const KeyT* in, KeyT* buf0, 
         a.num_chunks      = static_cast<uint32_t>(pl.num_chunks);
         a.digit           = pt.d[p];
         a.use_tma         = ((s->flags & RS_NO_TMA) == 0) && all_aligned;
-        cudaError_t e = has_vals ? launch_pass<KeyT, true>(s->ctx, st, a) : launch_pass<KeyT, false>(s->ctx, st, a);
+        cudaError_t e = has_vals ? launch_pass<KeyT, true>(s->ctx, st, a, s->atomic_rank)
+                                 : launch_pass<KeyT, false>(s->ctx, st, a, s->atomic_rank);
         if (e != cudaSuccess) return fail(RS_CALCULATION_FAILED, "onesweep launch", e);
         s->launches++;
     }
@@ -547,14 +568,33 @@ int rs_context_create(int device, rs_context* out) {
     RS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device), RS_INITIALIZATION_FAILED);
     RS_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device), RS_INITIALIZATION_FAILED);
     if (major != 10) return fail(RS_INITIALIZATION_FAILED, "librsb200 is built for sm_100a (B200) only");
-    rs_context c = new (std::nothrow) rs_context_s{device, sms, smem};
+    rs_context c = new (std::nothrow) rs_context_s{device, sms, smem, 0};
     if (!c) return fail(RS_INITIALIZATION_FAILED, "out of host memory");
+    {   // self-test behind the atomic ranking mode (a few hundred microseconds; see rs_kernels.cuh)
+        unsigned long long* d_bad = nullptr;
+        unsigned long long  h_bad = 1;
+        const char*         off   = getenv("RSB200_NO_ATOMIC_RANK");
+        if (!(off && off[0] == '1') && cudaMalloc(reinterpret_cast<void**>(&d_bad), sizeof h_bad) == cudaSuccess) {
+            cudaMemset(d_bad, 0, sizeof h_bad);
+            rs_atomic_order_selftest_kernel<<<sms, 256>>>(d_bad, 4096);
+            if (cudaMemcpy(&h_bad, d_bad, sizeof h_bad, cudaMemcpyDeviceToHost) != cudaSuccess) h_bad = 1;
+            cudaFree(d_bad);
+            (void)cudaGetLastError();
+        }
+        c->atomic_rank_ok = (h_bad == 0) ? 1 : 0;
+    }
     *out = c;
     return RS_OK;
 }
 
 int rs_context_destroy(rs_context ctx) {
     delete ctx;
+    return RS_OK;
+}
+
+int rs_context_atomic_rank(rs_context ctx, int* enabled) {
+    if (!ctx || !enabled) return fail(RS_INITIALIZATION_FAILED, "null argument");
+    *enabled = ctx->atomic_rank_ok;
     return RS_OK;
 }
 
@@ -627,6 +667,7 @@ int rs_sorter_create(rs_context ctx, rs_key_type type, uint64_t max_keys, uint32
     s->key_bytes = (type == RS_KEY_U32 || type == RS_KEY_I32) ? 4 : 8;
     s->is_signed = (type == RS_KEY_I32 || type == RS_KEY_I64);
     s->has_vals  = (flags & RS_WITH_PERMUTATION) != 0;
+    s->atomic_rank = ctx->atomic_rank_ok && !(flags & RS_NO_ATOMIC_RANK);
     stat_reset(s->rt.time_histo); stat_reset(s->rt.time_scan); stat_reset(s->rt.time_reorder);
     stat_reset(s->rt.time_paste); stat_reset(s->rt.time_total);
     if (s->has_vals && max_keys > (1ull << 32)) {
@@ -636,8 +677,8 @@ int rs_sorter_create(rs_context ctx, rs_key_type type, uint64_t max_keys, uint32
     const uint64_t alloc_keys = std::max<uint64_t>(max_keys, 1);
     // scratch sized for the worst plan: the keys-only tile may differ from the key+value tile
     const int full_passes = static_cast<int>(s->key_bytes);
-    size_t need = std::max(make_plan(alloc_keys, s->key_bytes, false, full_passes).total,
-                           make_plan(alloc_keys, s->key_bytes, true, full_passes).total);
+    size_t need = std::max(make_plan(alloc_keys, s->key_bytes, false, s->atomic_rank, full_passes).total,
+                           make_plan(alloc_keys, s->key_bytes, true, s->atomic_rank, full_passes).total);
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&s->scratch), need);
     if (e != cudaSuccess) { delete s; return fail(RS_INITIALIZATION_FAILED, "cudaMalloc scratch", e); }
     s->scratch_bytes = need;

@@ -343,22 +343,30 @@ rs_scan_kernel(const unsigned long long* __restrict__ hist, unsigned long long* 
 // ------------------------------------------------------------------------------------------------
 // Onesweep pass: persistent CTAs take tile ids from an atomic dispenser, prefetch the NEXT tile's
 // keys into shared memory with a 1-D bulk async copy (TMA) while ranking the current one, rank the
-// digits half-warp by half-warp, resolve the tile's global digit offsets with a decoupled look-back
-// over status words, stage the keys (and values) in shared memory in ranked order and write them
-// out in coalesced per-digit runs.  Stable.
+// digits group by group, resolve the tile's global digit offsets with a decoupled look-back over
+// status words, stage the keys (and values) in shared memory in ranked order and write them out in
+// coalesced per-digit runs.  Stable.
 //
-// Ranking (measured on B200, tools/ubench.cu and ncu): MATCH.ANY costs ~1.4 cycles per DISTINCT
-// value per SM (45 cycles for random 8-bit digits; ADU pipe 78 % busy in the first version), eight
-// ballots cost 17 and share the MIO path with the LSU.  Cheapest is a shared-memory lane bitmap:
-// every lane ORs its lane bit into word [group][digit], reads the word back, the lowest lane of
-// each match group clears the bitmap and bumps the group's running count.  The kernel is bound by
-// shared-memory wavefronts (LSU data pipe ~88 % busy), so the table word is ONE 32-bit word
-// {count:16 | bitmap:16} per (half-warp, digit): three 32-bit accesses per key instead of one
-// 32-bit and two 64-bit ones (the 64-bit layout halves the banks a 32-bit access can use).
-// A half-warp owns 16*KPT consecutive keys of the tile and walks them 16 at a time, so the order of
-// processing is the index order and ranks are stable.  Rows whose 16 digits are all equal (Zeros,
-// the high digits of Range) would serialise on one word, so they take a shortcut decided by one
-// shuffle + vote per row.
+// The kernel is bound by shared-memory wavefronts (LSU data pipe ~89 % busy, ncu), so ranking is
+// chosen by how many data-dependent shared accesses it needs per key.  Measured on B200
+// (tools/ubench.cu, tools/atomorder.cu, ncu): MATCH.ANY costs ~1.4 cycles per DISTINCT value per SM
+// (45 for random 8-bit digits), eight ballots cost 17 and make the kernel issue-bound.  Two modes:
+//
+//  ATOMIC_RANK = true  (default when the device passes the self-test of rs_context_create):
+//      rank = atomicAdd(&count[warp][digit], 1).  ONE access per key.  This is a stable rank only
+//      because the hardware serves the lanes of one warp instruction that hit the same shared word
+//      in ascending lane order -- not documented, so it is TESTED: tools/atomorder.cu saw 0
+//      violations in 6e9 warp rows on B200 (all-equal .. all-distinct digits, single-bank and
+//      conflict-free layouts, partial warps), and every context re-runs that test before it enables
+//      the mode; the parity tests compare keys AND the stable permutation bit-exactly.
+//  ATOMIC_RANK = false (fallback, RS_NO_ATOMIC_RANK): a shared-memory lane bitmap per
+//      (half-warp, digit), {count:16 | bitmap:16} in one 32-bit word: every lane ORs its lane bit
+//      in, reads the word back, the lowest lane of each match group clears the bitmap and bumps
+//      the count.  Three accesses per key; relies on nothing beyond the PTX memory model.
+//
+// A group (warp / half-warp) owns ROW*KPT consecutive keys of the tile and walks them ROW at a time,
+// so the order of processing is the index order.  Rows whose digits are all equal (Zeros, the high
+// digits of Range) would serialise on one word and take a warp-uniform shortcut.
 // Algorithmic traffic: sizeof(KeyT) read + sizeof(KeyT) written per key (+4+4 with values).
 // ------------------------------------------------------------------------------------------------
 template <typename KeyT>
@@ -380,18 +388,19 @@ struct OnesweepArgs {
     int                       use_tma;
 };
 
-template <typename KeyT, bool HAS_VALS, int THREADS, int KPT>
+template <typename KeyT, bool HAS_VALS, int THREADS, int KPT, bool ATOMIC_RANK>
 struct OnesweepSmem {
     static constexpr int    TILE   = THREADS * KPT;
     static constexpr int    NWARPS = THREADS / 32;
-    static constexpr int    NHALF  = NWARPS * 2;    // half-warp ranking groups
-    static constexpr int    PARTS  = THREADS / RADIX;  // threads per digit in the scan phase
+    static constexpr int    ROW    = ATOMIC_RANK ? 32 : 16;           // keys a ranking group handles per step
+    static constexpr int    GROUPS = THREADS / ROW;                   // warps or half-warps
+    static constexpr int    PARTS  = THREADS / RADIX;                 // threads per digit in the scan phase
     static constexpr size_t stage_bytes = sizeof(KeyT) * TILE;
     static constexpr size_t off_stage0  = 0;
     static constexpr size_t off_stage1  = off_stage0 + stage_bytes;
     static constexpr size_t off_vstage  = off_stage1 + stage_bytes;
     static constexpr size_t off_tab     = off_vstage + (HAS_VALS ? sizeof(uint32_t) * TILE : 0);
-    static constexpr size_t off_kptr    = off_tab + sizeof(uint32_t) * NHALF * RADIX;
+    static constexpr size_t off_kptr    = off_tab + sizeof(uint32_t) * GROUPS * RADIX;
     static constexpr size_t off_vptr    = off_kptr + sizeof(void*) * RADIX;
     static constexpr size_t off_ptot    = off_vptr + (HAS_VALS ? sizeof(void*) * RADIX : 0);
     static constexpr size_t off_wsum    = off_ptot + sizeof(uint32_t) * PARTS * RADIX;
@@ -400,28 +409,25 @@ struct OnesweepSmem {
     static constexpr size_t total       = off_tile + sizeof(uint32_t) * 4;
 };
 
-template <typename KeyT, bool HAS_VALS, int THREADS, int KPT, int MIN_BLOCKS>
+__device__ __forceinline__ uint32_t atoms_add_return(uint32_t* p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    return old;
+}
+
+template <typename KeyT, bool HAS_VALS, int THREADS, int KPT, int MIN_BLOCKS, bool ATOMIC_RANK>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
-    using L = OnesweepSmem<KeyT, HAS_VALS, THREADS, KPT>;
-    constexpr int TILE  = L::TILE;
-    constexpr int NHALF = L::NHALF;
-    constexpr int PARTS = L::PARTS;
-    constexpr int HPP   = NHALF / PARTS;  // half-warp tables per scan thread
-    static_assert(THREADS % RADIX == 0 && NHALF % PARTS == 0, "THREADS must be a multiple of 256");
+    using L = OnesweepSmem<KeyT, HAS_VALS, THREADS, KPT, ATOMIC_RANK>;
+    constexpr int TILE   = L::TILE;
+    constexpr int ROW    = L::ROW;
+    constexpr int GROUPS = L::GROUPS;
+    constexpr int PARTS  = L::PARTS;
+    constexpr int GPP    = GROUPS / PARTS;              // group tables per scan thread
+    constexpr int CSHIFT = ATOMIC_RANK ? 0 : 16;        // where the count / position lives in a table word
+    static_assert(THREADS % RADIX == 0 && GROUPS % PARTS == 0, "THREADS must be a multiple of 256");
     static_assert((sizeof(KeyT) * TILE) % 128 == 0, "stage must keep 128B alignment");
     static_assert(TILE <= 0xffff, "16-bit count / position fields");
-
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    KeyT* const        stage0  = reinterpret_cast<KeyT*>(smem_raw + L::off_stage0);  // stage s = stage0 + s*TILE
-    uint32_t* const    vstage  = reinterpret_cast<uint32_t*>(smem_raw + L::off_vstage);
-    uint32_t* const    tab     = reinterpret_cast<uint32_t*>(smem_raw + L::off_tab);   // [half-warp][digit] count<<16 | bitmap
-    KeyT** const       kptr    = reinterpret_cast<KeyT**>(smem_raw + L::off_kptr);     // [digit] -> keys_out run - tile pos
-    uint32_t** const   vptr    = reinterpret_cast<uint32_t**>(smem_raw + L::off_vptr);
-    uint32_t* const    ptot    = reinterpret_cast<uint32_t*>(smem_raw + L::off_ptot);  // [part][digit] partial digit totals
-    uint32_t* const    wsum    = reinterpret_cast<uint32_t*>(smem_raw + L::off_wsum);
-    uint64_t* const    mbar    = reinterpret_cast<uint64_t*>(smem_raw + L::off_mbar);
-    volatile uint32_t* sh_tile = reinterpret_cast<volatile uint32_t*>(smem_raw + L::off_tile);
 
     {   // constant digit: the pass is the identity -- nothing to do, or a plain copy to keep the ping-pong parity
         const uint32_t action = a.plan->action[a.pass];
@@ -439,17 +445,28 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
             return;
         }
     }
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    KeyT* const        stage0  = reinterpret_cast<KeyT*>(smem_raw + L::off_stage0);  // stage s = stage0 + s*TILE
+    uint32_t* const    vstage  = reinterpret_cast<uint32_t*>(smem_raw + L::off_vstage);
+    uint32_t* const    tab     = reinterpret_cast<uint32_t*>(smem_raw + L::off_tab);   // [group][digit]
+    KeyT** const       kptr    = reinterpret_cast<KeyT**>(smem_raw + L::off_kptr);     // [digit] -> keys_out run - tile pos
+    uint32_t** const   vptr    = reinterpret_cast<uint32_t**>(smem_raw + L::off_vptr);
+    uint32_t* const    ptot    = reinterpret_cast<uint32_t*>(smem_raw + L::off_ptot);  // [part][digit] partial digit totals
+    uint32_t* const    wsum    = reinterpret_cast<uint32_t*>(smem_raw + L::off_wsum);
+    uint64_t* const    mbar    = reinterpret_cast<uint64_t*>(smem_raw + L::off_mbar);
+    volatile uint32_t* sh_tile = reinterpret_cast<volatile uint32_t*>(smem_raw + L::off_tile);
+
     const int       tid   = threadIdx.x;
     const int       lane  = tid & 31;
-    const int       warp  = tid >> 5;
-    const int       l16   = lane & 15;
-    const int       hw    = warp * 2 + (lane >> 4);               // this lane's half-warp
-    const uint32_t  bit16 = 1u << l16;
-    const uint32_t  lt16  = bit16 - 1u;
+    const int       lig   = tid & (ROW - 1);               // lane within its ranking group
+    const int       grp   = tid / ROW;                     // this lane's ranking group
+    const uint32_t  bitg  = 1u << lig;
+    const uint32_t  ltg   = bitg - 1u;
     const DigitSpec ds    = a.digit;
     const uint32_t  full_tiles = static_cast<uint32_t>(a.n / TILE);  // tiles [0, full_tiles) are complete
-    uint32_t* const ht    = tab + hw * RADIX;
-    // scan-phase role: digit `sd`, half-warp tables [sp*HPP, sp*HPP + HPP)
+    uint32_t* const gt    = tab + grp * RADIX;
+    // scan-phase role: digit `sd`, group tables [sp*GPP, sp*GPP + GPP)
     const int       sd    = tid & (RADIX - 1);
     const int       sp    = tid / RADIX;
 
@@ -473,7 +490,7 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
     }
     // the tables start clean; every tile re-zeroes them itself after its scatter
 #pragma unroll
-    for (int j = 0; j < HPP; ++j) tab[(sp * HPP + j) * RADIX + sd] = 0u;
+    for (int j = 0; j < GPP; ++j) tab[(sp * GPP + j) * RADIX + sd] = 0u;
     __syncthreads();
 
     uint32_t phase_bits = 0;  // bit s = parity to wait for on mbar[s]
@@ -484,7 +501,7 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
         const bool     via_tma  = FULL && a.use_tma;
         const uint64_t tile_base = static_cast<uint64_t>(t) * TILE;
         const uint32_t valid    = FULL ? TILE : static_cast<uint32_t>(a.n - tile_base);
-        const uint32_t my_first = hw * (16 * KPT) + l16;  // half-warp-striped: item r sits at my_first + 16*r
+        const uint32_t my_first = grp * (ROW * KPT) + lig;  // group-striped: item r sits at my_first + ROW*r
         KeyT* const    stg      = stage0 + s * TILE;
 
         // ---- keys (and values) into registers -------------------------------------------------
@@ -493,11 +510,11 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
             mbar_wait(&mbar[s], (phase_bits >> s) & 1u);
             phase_bits ^= (1u << s);
 #pragma unroll
-            for (int r = 0; r < KPT; ++r) key[r] = stg[my_first + 16 * r];
+            for (int r = 0; r < KPT; ++r) key[r] = stg[my_first + ROW * r];
         } else {
 #pragma unroll
             for (int r = 0; r < KPT; ++r) {
-                const uint32_t i = my_first + 16 * r;
+                const uint32_t i = my_first + ROW * r;
                 key[r] = (FULL || i < valid) ? a.keys_in[tile_base + i] : static_cast<KeyT>(~static_cast<KeyT>(0));
             }
         }
@@ -505,58 +522,75 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
         if constexpr (HAS_VALS) {
 #pragma unroll
             for (int r = 0; r < KPT; ++r) {
-                const uint32_t i = my_first + 16 * r;
+                const uint32_t i = my_first + ROW * r;
                 val[r]           = (FULL || i < valid) ? a.vals_in[tile_base + i] : 0u;
             }
         }
 
-        // ---- rank within the half-warp ----------------------------------------------------------
-        uint32_t rk[(KPT + 1) / 2];  // two 16-bit ranks per register (rank < 16*KPT)
+        // ---- rank within the group -----------------------------------------------------------------
+        uint32_t rk[(KPT + 1) / 2];  // two 16-bit ranks per register (rank < ROW*KPT)
 #pragma unroll
         for (int r = 0; r < KPT; ++r) {
             uint32_t d = digit_of(key[r], ds);
-            if (!FULL && (my_first + 16 * r) >= valid) d = RADIX - 1;  // padding ranks last
+            if (!FULL && (my_first + ROW * r) >= valid) d = RADIX - 1;  // padding ranks last
             uint32_t my_rank;
-            // warp-uniform test "both half-warps hold 16 equal digits" (all masks stay compile-time constants)
-            const uint32_t d_first = __shfl_sync(0xffffffffu, d, lane & 16);
-            if (__all_sync(0xffffffffu, d == d_first)) {
-                // ranks follow the lane order, one lane per half-warp bumps the count
-                const uint32_t e = ht[d];
-                __syncwarp();
-                if (l16 == 0) ht[d] = e + (16u << 16);
-                my_rank = (e >> 16) + l16;
+            if constexpr (ATOMIC_RANK) {
+                int all_same;
+                __match_all_sync(0xffffffffu, d, &all_same);
+                if (all_same) {  // 32 equal digits would serialise on one word: ranks follow the lane order
+                    const uint32_t c = gt[d];
+                    __syncwarp();
+                    if (lane == 0) gt[d] = c + 32u;
+                    my_rank = c + lane;
+                } else {
+                    // same-word lanes are served in ascending lane order (self-tested, see the header comment),
+                    // so the returned count is the stable rank
+                    my_rank = atoms_add_return(&gt[d], 1u);
+                }
             } else {
-                atomicOr(&ht[d], bit16);
-                __syncwarp();
-                const uint32_t e = ht[d];
-                __syncwarp();
-                const uint32_t below = __popc(e & lt16);
-                if (below == 0) ht[d] = (e & 0xffff0000u) + (static_cast<uint32_t>(__popc(e & 0xffffu)) << 16);
-                my_rank = (e >> 16) + below;
+                // warp-uniform test "both half-warps hold 16 equal digits" (all masks stay compile-time constants)
+                const uint32_t d_first = __shfl_sync(0xffffffffu, d, lane & 16);
+                if (__all_sync(0xffffffffu, d == d_first)) {
+                    const uint32_t e = gt[d];
+                    __syncwarp();
+                    if (lig == 0) gt[d] = e + (16u << 16);
+                    my_rank = (e >> 16) + lig;
+                } else {
+                    atomicOr(&gt[d], bitg);
+                    __syncwarp();
+                    const uint32_t e = gt[d];
+                    __syncwarp();
+                    const uint32_t below = __popc(e & ltg);
+                    if (below == 0) gt[d] = (e & 0xffff0000u) + (static_cast<uint32_t>(__popc(e & 0xffffu)) << 16);
+                    my_rank = (e >> 16) + below;
+                }
             }
             __syncwarp();
             if (r & 1) rk[r >> 1] |= my_rank << 16; else rk[r >> 1] = my_rank;
         }
-        __syncthreads();  // (A) all half-warp counts final; every key of this stage is in registers
+        __syncthreads();  // (A) all group counts final; every key of this stage is in registers
 
-        // ---- scan: every thread owns digit sd of HPP half-warp tables ----------------------------
+        // ---- scan: every thread owns digit sd of GPP group tables ----------------------------------
         const uint32_t chunk          = t / a.tiles_per_chunk;
         const bool     first_in_chunk = (t % a.tiles_per_chunk) == 0;
-        uint32_t       pre[(HPP + 1) / 2];  // exclusive prefixes over this thread's tables, two 16-bit values per register
+        uint32_t       pre[(GPP + 1) / 2];  // exclusive prefixes over this thread's tables, two 16-bit values per register
         uint32_t       part_sum = 0;
 #pragma unroll
-        for (int j = 0; j < HPP; ++j) {
+        for (int j = 0; j < GPP; ++j) {
             if (j & 1) pre[j >> 1] |= part_sum << 16; else pre[j >> 1] = part_sum;
-            part_sum += tab[(sp * HPP + j) * RADIX + sd] >> 16;
+            part_sum += tab[(sp * GPP + j) * RADIX + sd] >> CSHIFT;
         }
-        ptot[sp * RADIX + sd] = part_sum;
-        __syncthreads();  // (B1)
-        uint32_t count = 0, before_part = 0;
+        uint32_t count = part_sum, before_part = 0;
+        if constexpr (PARTS > 1) {
+            ptot[sp * RADIX + sd] = part_sum;
+            __syncthreads();  // (B1)
+            count = 0;
 #pragma unroll
-        for (int q = 0; q < PARTS; ++q) {
-            const uint32_t v = ptot[q * RADIX + sd];
-            count += v;
-            before_part += (q < sp) ? v : 0u;
+            for (int q = 0; q < PARTS; ++q) {
+                const uint32_t v = ptot[q * RADIX + sd];
+                count += v;
+                before_part += (q < sp) ? v : 0u;
+            }
         }
         if (!FULL && sd == RADIX - 1) count -= (TILE - valid);
         uint32_t* my_status = a.status + static_cast<size_t>(t) * RADIX + sd;
@@ -567,24 +601,24 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
             const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += x;
         }
-        if (sp == 0 && lane == 31) wsum[warp] = incl;
+        if (sp == 0 && lane == 31) wsum[sd >> 5] = incl;
         __syncthreads();  // (B2)
         uint32_t woff = 0;
 #pragma unroll
         for (int w = 0; w < RADIX / 32; ++w) woff += (w < (sd >> 5)) ? wsum[w] : 0u;
         const uint32_t local_base = woff + incl - count;  // tile-local start of digit sd
 #pragma unroll
-        for (int j = 0; j < HPP; ++j)
-            tab[(sp * HPP + j) * RADIX + sd] =
-                (local_base + before_part + ((j & 1) ? (pre[j >> 1] >> 16) : (pre[j >> 1] & 0xffffu))) << 16;
-        __syncthreads();  // (C) tab[h][d] >> 16 = tile-local position of half-warp h's first key with digit d
+        for (int j = 0; j < GPP; ++j)
+            tab[(sp * GPP + j) * RADIX + sd] =
+                (local_base + before_part + ((j & 1) ? (pre[j >> 1] >> 16) : (pre[j >> 1] & 0xffffu))) << CSHIFT;
+        __syncthreads();  // (C) tab[g][d] >> CSHIFT = tile-local position of group g's first key with digit d
 
         // ---- scatter into shared memory in ranked order -----------------------------------------
 #pragma unroll
         for (int r = 0; r < KPT; ++r) {
             uint32_t d = digit_of(key[r], ds);
-            if (!FULL && (my_first + 16 * r) >= valid) d = RADIX - 1;
-            const uint32_t pos = (ht[d] >> 16) + ((r & 1) ? (rk[r >> 1] >> 16) : (rk[r >> 1] & 0xffffu));
+            if (!FULL && (my_first + ROW * r) >= valid) d = RADIX - 1;
+            const uint32_t pos = (gt[d] >> CSHIFT) + ((r & 1) ? (rk[r >> 1] >> 16) : (rk[r >> 1] & 0xffffu));
             stg[swz(pos)]      = key[r];
             if constexpr (HAS_VALS) vstage[swz(pos)] = val[r];
         }
@@ -632,7 +666,7 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
 
         // ---- re-zero the tables; coalesced per-digit runs out to global memory -------------------
 #pragma unroll
-        for (int j = 0; j < HPP; ++j) tab[(sp * HPP + j) * RADIX + sd] = 0u;
+        for (int j = 0; j < GPP; ++j) tab[(sp * GPP + j) * RADIX + sd] = 0u;
 #pragma unroll
         for (int i = 0; i < KPT; ++i) {
             const uint32_t p = i * THREADS + tid;
@@ -660,6 +694,40 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
             process_tile(std::false_type{}, t);
         s ^= 1;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Self-test behind ATOMIC_RANK: for random digit patterns (1 .. 256 distinct values, single-bank and
+// spread layouts, partial warps) every lane does old = atomicAdd(&cnt[d], 1) and checks
+// old == count_before + (number of lower lanes with the same d).  Any violation disables the mode.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rs_atomic_order_selftest_kernel(unsigned long long* violations, int iters) {
+    __shared__ uint32_t cnt[8][512];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = lane; i < 512; i += 32) cnt[warp][i] = 0;
+    __syncwarp();
+    uint32_t           v   = (tid * 7919u + blockIdx.x * 104729u) * 2654435761u + 12345u;
+    unsigned long long bad = 0;
+    const uint32_t     lt  = (1u << lane) - 1u;
+    const int          distincts[8] = {1, 2, 3, 5, 8, 16, 31, 256};
+    for (int it = 0; it < iters; ++it) {
+        v = v * 1664525u + 1013904223u;
+        const int      distinct = distincts[(it >> 3) & 7];
+        const int      stride   = (it & 1) ? 32 : ((it & 2) ? 33 : 1);
+        const uint32_t d        = (((v >> 9) % distinct) * stride) & 511;
+        const bool     active   = (it & 4) ? (((v >> 20) & 3) != 0) : true;
+        const uint32_t amask    = __ballot_sync(0xffffffffu, active);
+        const uint32_t before   = cnt[warp][d];
+        __syncwarp();
+        uint32_t old = 0;
+        if (active) old = atoms_add_return(&cnt[warp][d], 1u);
+        __syncwarp();
+        const uint32_t m = __match_any_sync(0xffffffffu, d) & amask;
+        if (active && old != before + __popc(m & lt)) ++bad;
+        __syncwarp();
+    }
+    if (bad) atomicAdd(violations, bad);
 }
 
 }  // namespace rsb

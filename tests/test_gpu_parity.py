@@ -101,6 +101,23 @@ def test_size_sweep_u32_key_value(rsb, gpu, oracle):
         assert np.array_equal(perm, np.argsort(data, kind="stable").astype(np.uint32)), k
 
 
+@pytest.mark.parametrize("t", KEY_TYPES)
+def test_ranking_modes_agree(rsb, gpu, oracle, t):
+    # default = one shared atomic per key (enabled by the context's lane-order self-test), fallback = lane bitmap
+    ctx, _ = gpu
+    assert ctx.atomic_rank, "the B200 passes the same-word atomic ordering self-test"
+    rng = np.random.default_rng(11)
+    n = 200003
+    few = rng.integers(0, 3, size=n).astype(numpy_dtype(t))          # long same-digit groups in every row
+    two = np.where(np.arange(n) % 2 == 0, 5, 70000).astype(numpy_dtype(t))
+    for data in (oracle.dataset("uniform", t, n, SEED), oracle.dataset("range", t, n), few, two):
+        a, pa, _ = host_sort(rsb, gpu, data, t, with_perm=True)
+        b, pb, _ = host_sort(rsb, gpu, data, t, with_perm=True, flags=rsb.RS_NO_ATOMIC_RANK)
+        want = np.argsort(data, kind="stable").astype(np.uint32)
+        assert np.array_equal(pa, want) and np.array_equal(pb, want)
+        assert np.array_equal(a, data[want]) and np.array_equal(b, a)
+
+
 def test_empty_input(rsb, gpu):
     got, perm, _ = host_sort(rsb, gpu, np.empty(0, dtype=np.uint32), "u32", with_perm=True)
     assert got.size == 0 and perm.size == 0

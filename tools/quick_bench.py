@@ -17,6 +17,7 @@ def main():
     kinds = args.get("kinds", "uniform,random,range,inverted,zeros").split(",")
     perm = int(args.get("perm", 0))
     notma = int(args.get("notma", 0))
+    noatomic = int(args.get("noatomic", 0))
     iters = int(args.get("iters", 5))
     n = 1 << log2n
     ctx = rsb.Context(0)
@@ -28,7 +29,7 @@ def main():
         bufs = [torch.empty(n, dtype=tdt, device="cuda") for _ in range(2)]
         vin = torch.arange(n, dtype=torch.int32, device="cuda") if perm else None
         vb = [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(2)] if perm else None
-        s = rsb.Sorter(ctx, t, n, rsb.RS_NO_KEY_BUFFERS | (rsb.RS_NO_TMA if notma else 0))
+        s = rsb.Sorter(ctx, t, n, rsb.RS_NO_KEY_BUFFERS | (rsb.RS_NO_TMA if notma else 0) | (rsb.RS_NO_ATOMIC_RANK if noatomic else 0))
         for kind in kinds:
             ctx.fill_dataset(st, t, kind, d_in.data_ptr(), n)
             for _ in range(2):
@@ -50,7 +51,7 @@ def main():
             chk = ctx.check(st, t, bufs[r].data_ptr(), n)
             passes = kb
             bpk = kb + passes * 2 * (kb + (4 if perm else 0))
-            print(f"{t} {kind:9s} n=2^{log2n} perm={perm} notma={notma}: {ms:8.3f} ms  {n / ms / 1e6:7.2f} Gkeys/s  "
+            print(f"{t} {kind:9s} n=2^{log2n} perm={perm} notma={notma} atomic={int(ctx.atomic_rank and not noatomic)}: {ms:8.3f} ms  {n / ms / 1e6:7.2f} Gkeys/s  "
                   f"{bpk * n / ms / 1e6:7.1f} GB/s algorithmic | hist {rt['time_histo']['avg']:.3f} scan "
                   f"{rt['time_scan']['avg']:.3f} passes {rt['time_reorder']['avg']:.3f} "
                   f"({rt['time_reorder']['avg'] / passes:.3f}/pass) total {rt['time_total']['avg']:.3f} "
