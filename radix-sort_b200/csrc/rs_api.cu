@@ -112,19 +112,35 @@ struct TileCfg;
 #define RS_U32_KPT 24
 #define RS_U32_MINB 3
 #endif
+// atomic ranking mode (default on B200): larger tiles pay (fewer look-backs and table scans per key)
 #ifndef RS_U32A_THREADS
-#define RS_U32A_THREADS 256
-#define RS_U32A_KPT 24
-#define RS_U32A_MINB 3
+#define RS_U32A_THREADS 512
+#define RS_U32A_KPT 20
+#define RS_U32A_MINB 2
+#endif
+#ifndef RS_U32VA_THREADS
+#define RS_U32VA_THREADS 512
+#define RS_U32VA_KPT 14
+#define RS_U32VA_MINB 2
+#endif
+#ifndef RS_U64A_THREADS
+#define RS_U64A_THREADS 512
+#define RS_U64A_KPT 10
+#define RS_U64A_MINB 2
+#endif
+#ifndef RS_U64VA_THREADS
+#define RS_U64VA_THREADS 512
+#define RS_U64VA_KPT 8
+#define RS_U64VA_MINB 2
 #endif
 template <> struct TileCfg<uint32_t, false, false> { static constexpr int THREADS = RS_U32_THREADS, KPT = RS_U32_KPT, MINB = RS_U32_MINB; };
 template <> struct TileCfg<uint32_t, true,  false> { static constexpr int THREADS = 512, KPT = 12, MINB = 2; };
 template <> struct TileCfg<uint64_t, false, false> { static constexpr int THREADS = 512, KPT = 8,  MINB = 2; };
 template <> struct TileCfg<uint64_t, true,  false> { static constexpr int THREADS = 512, KPT = 8,  MINB = 2; };
 template <> struct TileCfg<uint32_t, false, true>  { static constexpr int THREADS = RS_U32A_THREADS, KPT = RS_U32A_KPT, MINB = RS_U32A_MINB; };
-template <> struct TileCfg<uint32_t, true,  true>  { static constexpr int THREADS = 512, KPT = 12, MINB = 2; };
-template <> struct TileCfg<uint64_t, false, true>  { static constexpr int THREADS = 512, KPT = 8,  MINB = 2; };
-template <> struct TileCfg<uint64_t, true,  true>  { static constexpr int THREADS = 512, KPT = 8,  MINB = 2; };
+template <> struct TileCfg<uint32_t, true,  true>  { static constexpr int THREADS = RS_U32VA_THREADS, KPT = RS_U32VA_KPT, MINB = RS_U32VA_MINB; };
+template <> struct TileCfg<uint64_t, false, true>  { static constexpr int THREADS = RS_U64A_THREADS, KPT = RS_U64A_KPT, MINB = RS_U64A_MINB; };
+template <> struct TileCfg<uint64_t, true,  true>  { static constexpr int THREADS = RS_U64VA_THREADS, KPT = RS_U64VA_KPT, MINB = RS_U64VA_MINB; };
 
 template <typename KeyT, bool HAS_VALS, bool ATOMIC>
 static constexpr int tile_of() { return TileCfg<KeyT, HAS_VALS, ATOMIC>::THREADS * TileCfg<KeyT, HAS_VALS, ATOMIC>::KPT; }

@@ -353,7 +353,9 @@ rs_scan_kernel(const unsigned long long* __restrict__ hist, unsigned long long* 
 // (45 for random 8-bit digits), eight ballots cost 17 and make the kernel issue-bound.  Two modes:
 //
 //  ATOMIC_RANK = true  (default when the device passes the self-test of rs_context_create):
-//      rank = atomicAdd(&count[warp][digit], 1).  ONE access per key.  This is a stable rank only
+//      count first (atomicAdd(&count[warp][digit], 1), no return value), publish the tile's digit
+//      counts, turn the counts into tile positions, then position = atomicAdd(&pos[warp][digit], 1)
+//      while scattering.  Two accesses per key, no rank registers.  The position is stable only
 //      because the hardware serves the lanes of one warp instruction that hit the same shared word
 //      in ascending lane order -- not documented, so it is TESTED: tools/atomorder.cu saw 0
 //      violations in 6e9 warp rows on B200 (all-equal .. all-distinct digits, single-bank and
@@ -428,6 +430,7 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
     static_assert(THREADS % RADIX == 0 && GROUPS % PARTS == 0, "THREADS must be a multiple of 256");
     static_assert((sizeof(KeyT) * TILE) % 128 == 0, "stage must keep 128B alignment");
     static_assert(TILE <= 0xffff, "16-bit count / position fields");
+    static_assert(KPT <= 32, "uniform_rows is a 32-bit mask");
 
     {   // constant digit: the pass is the identity -- nothing to do, or a plain copy to keep the ping-pong parity
         const uint32_t action = a.plan->action[a.pass];
@@ -527,27 +530,25 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
             }
         }
 
-        // ---- rank within the group -----------------------------------------------------------------
-        uint32_t rk[(KPT + 1) / 2];  // two 16-bit ranks per register (rank < ROW*KPT)
+        // ---- ATOMIC_RANK: count now (so the tile's digit counts can be published early), rank while scattering;
+        //      bitmap mode: rank now -------------------------------------------------------------------------------
+        uint32_t rk[ATOMIC_RANK ? 1 : (KPT + 1) / 2];  // bitmap mode: two 16-bit ranks per register (rank < ROW*KPT)
+        uint32_t uniform_rows = 0;                       // atomic mode: bit r = all 32 digits of row r are equal
 #pragma unroll
         for (int r = 0; r < KPT; ++r) {
             uint32_t d = digit_of(key[r], ds);
             if (!FULL && (my_first + ROW * r) >= valid) d = RADIX - 1;  // padding ranks last
-            uint32_t my_rank;
             if constexpr (ATOMIC_RANK) {
                 int all_same;
                 __match_all_sync(0xffffffffu, d, &all_same);
-                if (all_same) {  // 32 equal digits would serialise on one word: ranks follow the lane order
-                    const uint32_t c = gt[d];
-                    __syncwarp();
-                    if (lane == 0) gt[d] = c + 32u;
-                    my_rank = c + lane;
+                if (all_same) {  // 32 equal digits would serialise on one word: one lane counts them all
+                    uniform_rows |= 1u << r;
+                    if (lane == 0) atomicAdd(&gt[d], 32u);
                 } else {
-                    // same-word lanes are served in ascending lane order (self-tested, see the header comment),
-                    // so the returned count is the stable rank
-                    my_rank = atoms_add_return(&gt[d], 1u);
+                    atomicAdd(&gt[d], 1u);
                 }
             } else {
+                uint32_t my_rank;
                 // warp-uniform test "both half-warps hold 16 equal digits" (all masks stay compile-time constants)
                 const uint32_t d_first = __shfl_sync(0xffffffffu, d, lane & 16);
                 if (__all_sync(0xffffffffu, d == d_first)) {
@@ -564,9 +565,9 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
                     if (below == 0) gt[d] = (e & 0xffff0000u) + (static_cast<uint32_t>(__popc(e & 0xffffu)) << 16);
                     my_rank = (e >> 16) + below;
                 }
+                __syncwarp();
+                if (r & 1) rk[r >> 1] |= my_rank << 16; else rk[r >> 1] = my_rank;
             }
-            __syncwarp();
-            if (r & 1) rk[r >> 1] |= my_rank << 16; else rk[r >> 1] = my_rank;
         }
         __syncthreads();  // (A) all group counts final; every key of this stage is in registers
 
@@ -618,8 +619,22 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
         for (int r = 0; r < KPT; ++r) {
             uint32_t d = digit_of(key[r], ds);
             if (!FULL && (my_first + ROW * r) >= valid) d = RADIX - 1;
-            const uint32_t pos = (gt[d] >> CSHIFT) + ((r & 1) ? (rk[r >> 1] >> 16) : (rk[r >> 1] & 0xffffu));
-            stg[swz(pos)]      = key[r];
+            uint32_t pos;
+            if constexpr (ATOMIC_RANK) {
+                // gt[d] is the running tile position of (this warp, digit d).  Lanes that hit the same word are served
+                // in ascending lane order (self-tested, see the header comment), so the returned value is the stable
+                // position of this key.
+                if (uniform_rows & (1u << r)) {
+                    uint32_t c = 0;
+                    if (lane == 0) c = atoms_add_return(&gt[d], 32u);
+                    pos = __shfl_sync(0xffffffffu, c, 0) + lane;
+                } else {
+                    pos = atoms_add_return(&gt[d], 1u);
+                }
+            } else {
+                pos = (gt[d] >> CSHIFT) + ((r & 1) ? (rk[r >> 1] >> 16) : (rk[r >> 1] & 0xffffu));
+            }
+            stg[swz(pos)] = key[r];
             if constexpr (HAS_VALS) vstage[swz(pos)] = val[r];
         }
 

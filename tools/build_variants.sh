@@ -1,13 +1,13 @@
 #!/bin/bash
-# Developer A/B builds of librsb200.so with different u32 keys-only tile shapes -> gpurun_variants/*.so
-# usage: tools/build_variants.sh "256 32 2" "256 16 4" ...   (THREADS KPT MIN_BLOCKS)
+# Developer A/B builds of librsb200.so with different tile shapes of the atomic ranking mode -> variants/*.so
+# usage: tools/build_variants.sh "U32A 512 20 2" "U32VA 512 14 2" "U64A 512 10 2" ...   (CFG THREADS KPT MIN_BLOCKS)
 set -e
 cd "$(dirname "$0")/../radix-sort_b200/csrc"
 mkdir -p ../../variants
 for cfg in "$@"; do
   set -- $cfg
-  out=../../variants/librsb200_t$1_k$2_b$3.so
+  out=../../variants/librsb200_$1_t$2_k$3_b$4.so
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -diag-suppress 177 \
-       -DRS_U32_THREADS=$1 -DRS_U32_KPT=$2 -DRS_U32_MINB=$3 $EXTRA -Xptxas -v -shared -o $out rs_api.cu 2> /tmp/variant_ptxas.log
-  echo "$out: $(grep -A2 'onesweep_kernelIjLb0E' /tmp/variant_ptxas.log | grep -E 'registers|spill' | sed 's/ptxas info    : //' | tr '\n' ' ')"
+       -DRS_$1_THREADS=$2 -DRS_$1_KPT=$3 -DRS_$1_MINB=$4 $EXTRA -Xptxas -v -shared -o $out rs_api.cu 2> /tmp/variant_ptxas.log
+  echo "$out: $(grep -A2 "ELi$2ELi$3ELi$4ELb1" /tmp/variant_ptxas.log | grep -E 'registers|spill' | sed 's/ptxas info    : //' | tr '\n' ' ' | cut -c1-300)"
 done
