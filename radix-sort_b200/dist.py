@@ -1,7 +1,7 @@
 """Multi-GPU sort on one NVSwitch box: one process per GPU (torch.distributed), keys-only.
 
 Path (BASELINE.json north_star): every GPU sorts its shard with the local onesweep,
-MSD splitter histograms (16 bits per level) are all-reduced, every rank computes the same exact
+MSD splitter histograms (11 bits per refinement round) are all-reduced, every rank computes the same exact
 splitters (ties on a splitter value are split by count -- equal keys are indistinguishable), key
 ranges are exchanged with ONE all-to-all-v over NVLink (NCCL), and every GPU sorts what it received.
 Afterwards rank r holds exactly its share of the global order: keys(r) <= keys(r+1), and the
@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import numpy as np
 
-LEVEL_BITS = 16
+LEVEL_BITS = 11   # splitter refinement fan-out per round: 2048 sub-ranges (32-bit keys: 11 + 11 + 10 bits)
 
 
 def _key_bits(key_type: str) -> int:
@@ -149,17 +149,19 @@ def plan_exchange(sorted_keys, ops, dist, key_type: str, group=None, device=None
     targets = [(j * n_total) // world for j in range(1, world)]  # global rank of the first key of rank j
     prefix = [0] * (world - 1)   # per splitter: ordered-unsigned key bits resolved so far
     below = [0] * (world - 1)    # per splitter: number of keys globally below `prefix`
-    levels = bits // LEVEL_BITS
-    fan = 1 << LEVEL_BITS
-    for level in range(levels):
-        shift = bits - LEVEL_BITS * (level + 1)
+    resolved = 0                 # key bits (from the top) already fixed in every splitter prefix
+    level = 0
+    while resolved < bits:
+        width = min(LEVEL_BITS, bits - resolved)
+        fan = 1 << width
+        shift = bits - resolved - width
         bases = [0] if level == 0 else prefix      # level 0: one histogram serves every splitter
         steps = np.arange(fan + 1, dtype=np.uint64) << np.uint64(shift)   # uint64 wrap-around == mod 2^64
         q = np.stack([np.uint64(b) + steps for b in bases])
         is_top = np.zeros(q.shape, dtype=bool)
         is_top[:, -1] = [b + (fan << shift) >= top for b in bases]         # the last boundary may be `top` itself
         pos = positions(q.reshape(-1), is_top.reshape(-1)).reshape(q.shape)
-        counts = allreduce_np(np.diff(pos, axis=1))   # [len(bases)][65536] global sub-range counts
+        counts = allreduce_np(np.diff(pos, axis=1))   # [len(bases)][fan] global sub-range counts
         for j in range(world - 1):
             c = counts[0 if level == 0 else j]
             cum = below[j] + np.concatenate(([0], np.cumsum(c)))
@@ -167,6 +169,8 @@ def plan_exchange(sorted_keys, ops, dist, key_type: str, group=None, device=None
             b = min(max(b, 0), fan - 1)
             prefix[j] += b << shift
             below[j] = int(cum[b])
+        resolved += width
+        level += 1
     # prefix[j] is now an exact key value v_j; the copies of v_j are split by count, in rank order
     pairs = [x for j in range(world - 1) for x in (prefix[j], prefix[j] + 1)]
     pos = positions(np.array([x & 0xFFFFFFFFFFFFFFFF for x in pairs], dtype=np.uint64),
