@@ -149,6 +149,10 @@ int rs_sorter_sort(rs_sorter s, rs_stream st, uint64_t n);
 /* D2H of the sorted keys / permutation; blocks until done. Either pointer may be NULL. */
 int rs_sorter_download(rs_sorter s, rs_stream st, void* h_keys_out, uint32_t* h_perm_out, uint64_t n);
 
+/* Same copies, enqueued only: the host buffers (pinned, rs_host_alloc) are valid after rs_stream_sync(st).
+ * Lets a caller overlap the download of one batch with the upload of the next on a second stream. */
+int rs_sorter_download_async(rs_sorter s, rs_stream st, void* h_keys_out, uint32_t* h_perm_out, uint64_t n);
+
 /* D2H of the digit histogram table of the last sort: passes x 256 uint64 counts (pass-major).
  * Counterpart of the reference's `histograms`/`globsum` read-backs (src/RadixSortGPU.cpp:411-428),
  * whose contents the reference never asserts. Blocks. Returns number of passes in *passes. */

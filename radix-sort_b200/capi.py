@@ -94,6 +94,7 @@ def load_library():
         "rs_sorter_upload": ([vp, vp, vp, vp, u64], i),
         "rs_sorter_sort": ([vp, vp, u64], i),
         "rs_sorter_download": ([vp, vp, vp, vp, u64], i),
+        "rs_sorter_download_async": ([vp, vp, vp, vp, u64], i),
         "rs_sorter_download_histograms": ([vp, vp, vp, C.c_size_t, C.POINTER(i)], i),
         "rs_sorter_sort_device": ([vp, vp, vp, vp, vp, vp, vp, vp, u64, i, i, C.POINTER(i)], i),
         "rs_sorter_runtimes": ([vp, C.POINTER(_Runtimes)], i),
@@ -283,6 +284,11 @@ class Sorter:
     def download(self, stream, h_keys_out, h_perm_out=None, n=None):
         n = len(h_keys_out) if n is None else n
         _check(self.lib.rs_sorter_download(self.handle, stream.handle, _addr(h_keys_out), _addr(h_perm_out), n))
+
+    def download_async(self, stream, h_keys_out, h_perm_out=None, n=None):
+        """Enqueue the copies only; the (pinned) host buffers are valid after stream.sync()."""
+        n = len(h_keys_out) if n is None else n
+        _check(self.lib.rs_sorter_download_async(self.handle, stream.handle, _addr(h_keys_out), _addr(h_perm_out), n))
 
     def download_histograms(self, stream):
         buf = np.zeros(8 * 256, dtype=np.uint64)

@@ -895,6 +895,23 @@ int rs_sorter_download(rs_sorter s, rs_stream st, void* h_keys_out, uint32_t* h_
     return RS_OK;
 }
 
+int rs_sorter_download_async(rs_sorter s, rs_stream st, void* h_keys_out, uint32_t* h_perm_out, uint64_t n) {
+    if (!s || !st) return fail(RS_DATA_DOWNLOAD_FAILED, "null argument");
+    if (!s->keys[0]) return fail(RS_DATA_DOWNLOAD_FAILED, "sorter has no key buffers");
+    if (n > s->max_keys) return fail(RS_DATA_DOWNLOAD_FAILED, "n exceeds max_keys");
+    RS_CUDA(cudaSetDevice(s->ctx->device), RS_DATA_DOWNLOAD_FAILED);
+    const int r = s->result_index;
+    if (n && h_keys_out)
+        RS_CUDA(cudaMemcpyAsync(h_keys_out, s->keys[r], n * s->key_bytes, cudaMemcpyDeviceToHost, st->st),
+                RS_DATA_DOWNLOAD_FAILED);
+    if (n && h_perm_out) {
+        if (!s->has_vals) return fail(RS_DATA_DOWNLOAD_FAILED, "sorter was created without RS_WITH_PERMUTATION");
+        RS_CUDA(cudaMemcpyAsync(h_perm_out, s->vals[r], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st->st),
+                RS_DATA_DOWNLOAD_FAILED);
+    }
+    return RS_OK;
+}
+
 int rs_sorter_download_histograms(rs_sorter s, rs_stream st, uint64_t* h_hist, size_t capacity, int* passes) {
     if (!s || !st || !h_hist) return fail(RS_DATA_DOWNLOAD_FAILED, "null argument");
     RS_CUDA(cudaSetDevice(s->ctx->device), RS_DATA_DOWNLOAD_FAILED);
