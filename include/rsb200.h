@@ -82,6 +82,7 @@ typedef enum rs_dataset_kind {
 #define RS_NO_PROFILE       0x4u /* do not record per-phase CUDA events in rs_sorter_sort        */
 #define RS_NO_KEY_BUFFERS   0x8u /* allocate only scratch; use rs_sorter_sort_device exclusively */
 #define RS_NO_PASS_SKIP     0x10u /* run every pass even when its digit is the same for all keys       */
+#define RS_NO_SMALL_PATH    0x40u /* always take the multi-kernel path, even for inputs one CTA could sort alone    */
 #define RS_NO_ATOMIC_RANK   0x20u /* rank with the shared-memory lane bitmap even if the atomic mode is available */
 
 typedef struct rs_context_s* rs_context;

@@ -18,7 +18,7 @@ _LIB_PATH = os.environ.get("RSB200_LIB") or os.path.join(HERE, "librsb200.so")
 KEY_TYPES = {"u32": 0, "i32": 1, "u64": 2, "i64": 3}
 _NP = {"u32": np.uint32, "i32": np.int32, "u64": np.uint64, "i64": np.int64}
 DATASET_KINDS = {"zeros": 0, "range": 1, "inverted": 2, "uniform": 3, "random": 4}
-RS_WITH_PERMUTATION, RS_NO_TMA, RS_NO_PROFILE, RS_NO_KEY_BUFFERS, RS_NO_PASS_SKIP, RS_NO_ATOMIC_RANK = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
+RS_WITH_PERMUTATION, RS_NO_TMA, RS_NO_PROFILE, RS_NO_KEY_BUFFERS, RS_NO_PASS_SKIP, RS_NO_ATOMIC_RANK, RS_NO_SMALL_PATH = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40
 
 _lib = None
 

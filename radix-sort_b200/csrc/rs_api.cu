@@ -308,6 +308,47 @@ static int sort_typed(rs_sorter s, cudaStream_t st, const KeyT* in, KeyT* buf0, 
     if (pl.total > s->scratch_bytes) return fail(RS_CALCULATION_FAILED, "n exceeds the sorter's max_keys (scratch too small)");
     if (pl.num_tiles >= (1ull << 32)) return fail(RS_CALCULATION_FAILED, "too many tiles");
 
+    // ---- small inputs: one launch of one CTA does every pass in shared memory ---------------------------------
+    if (n <= static_cast<uint64_t>(SMALL_CAP) && s->atomic_rank && !segments && !(s->flags & RS_NO_SMALL_PATH)) {
+        EventQuad sq{};
+        if (profile) {
+            if (!s->free_events.empty()) { sq = s->free_events.back(); s->free_events.pop_back(); }
+            else for (auto& e : sq.e) RS_CUDA(cudaEventCreate(&e), RS_CALCULATION_FAILED);
+            for (int i = 0; i < 3; ++i) RS_CUDA(cudaEventRecord(sq.e[i], st), RS_CALCULATION_FAILED);
+        }
+        KeyT*     kout = (((pt.num_passes - 1) & 1) == 0) ? buf0 : buf1;
+        uint32_t* vout = (((pt.num_passes - 1) & 1) == 0) ? vbuf0 : vbuf1;
+        auto* hist_s = reinterpret_cast<unsigned long long*>(s->scratch + pl.off_hist);
+        auto* plan_s = reinterpret_cast<SortPlanDev*>(s->scratch + pl.off_plan);
+        const int allow = (s->flags & RS_NO_PASS_SKIP) ? 0 : 1;
+        cudaError_t e;
+        if (has_vals) {
+            auto kern = rs_small_sort_kernel<KeyT, true>;
+            static thread_local bool cfg = false;
+            if (!cfg) { RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SmallSmem<KeyT, true>::total)), RS_CALCULATION_FAILED); cfg = true; }
+            kern<<<1, SMALL_THREADS, SmallSmem<KeyT, true>::total, st>>>(in, kout, vin, vout, static_cast<uint32_t>(n), pt, hist_s, plan_s, allow);
+            e = cudaGetLastError();
+        } else {
+            auto kern = rs_small_sort_kernel<KeyT, false>;
+            static thread_local bool cfg = false;
+            if (!cfg) { RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SmallSmem<KeyT, false>::total)), RS_CALCULATION_FAILED); cfg = true; }
+            kern<<<1, SMALL_THREADS, SmallSmem<KeyT, false>::total, st>>>(in, kout, nullptr, nullptr, static_cast<uint32_t>(n), pt, hist_s, plan_s, allow);
+            e = cudaGetLastError();
+        }
+        if (e != cudaSuccess) return fail(RS_CALCULATION_FAILED, "small sort launch", e);
+        s->launches++;
+        if (profile) {
+            RS_CUDA(cudaEventRecord(sq.e[3], st), RS_CALCULATION_FAILED);
+            s->pending.push_back(sq);
+        }
+        s->last_passes      = pt.num_passes;
+        s->last_chunks      = 1;
+        s->last_hist_offset = pl.off_hist;
+        s->last_plan_offset = pl.off_plan;
+        if (result_index) *result_index = (pt.num_passes - 1) & 1;
+        return RS_OK;
+    }
+
     EventQuad q{};
     if (profile) {
         if (!s->free_events.empty()) {

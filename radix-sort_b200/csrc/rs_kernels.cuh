@@ -712,6 +712,137 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Small inputs (n <= SMALL_CAP): the whole sort in ONE launch of ONE CTA, all passes in shared memory
+// (the general path costs a memset and 2 + passes launches, ~45 us, whatever n is).  Same ranking as
+// the atomic mode of rs_onesweep_kernel (count, scan, position atomic while scattering), same
+// skipping of constant-digit passes, same digit-histogram and plan read-backs.  Only used when the
+// context passed the atomic-order self-test.
+// ------------------------------------------------------------------------------------------------
+constexpr int SMALL_THREADS = 512;
+constexpr int SMALL_KPT     = 8;
+constexpr int SMALL_CAP     = SMALL_THREADS * SMALL_KPT;  // 4096 keys
+
+template <typename KeyT, bool HAS_VALS>
+struct SmallSmem {
+    static constexpr size_t off_keys = 0;
+    static constexpr size_t off_vals = off_keys + 2 * sizeof(KeyT) * SMALL_CAP;
+    static constexpr size_t off_tab  = off_vals + (HAS_VALS ? 2 * sizeof(uint32_t) * SMALL_CAP : 0);
+    static constexpr size_t off_wsum = off_tab + sizeof(uint32_t) * (SMALL_THREADS / 32) * RADIX;
+    static constexpr size_t total    = off_wsum + sizeof(uint32_t) * 16;
+};
+
+template <typename KeyT, bool HAS_VALS>
+__global__ void __launch_bounds__(SMALL_THREADS, 1)
+rs_small_sort_kernel(const KeyT* in, KeyT* out, const uint32_t* vin, uint32_t* vout,  // `out` may alias `in`
+                     uint32_t n, PassTable pt, unsigned long long* __restrict__ hist,
+                     SortPlanDev* __restrict__ plan, int allow_skip) {
+    using L = SmallSmem<KeyT, HAS_VALS>;
+    constexpr int NW = SMALL_THREADS / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    KeyT* const     kbuf = reinterpret_cast<KeyT*>(smem_raw + L::off_keys);      // [2][SMALL_CAP]
+    uint32_t* const vbuf = reinterpret_cast<uint32_t*>(smem_raw + L::off_vals);  // [2][SMALL_CAP]
+    uint32_t* const tab  = reinterpret_cast<uint32_t*>(smem_raw + L::off_tab);   // [warp][digit]
+    uint32_t* const wsum = reinterpret_cast<uint32_t*>(smem_raw + L::off_wsum);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t* const gt = tab + warp * RADIX;
+
+    for (uint32_t i = tid; i < SMALL_CAP; i += SMALL_THREADS) {
+        kbuf[i] = (i < n) ? in[i] : static_cast<KeyT>(~static_cast<KeyT>(0));
+        if constexpr (HAS_VALS) vbuf[i] = (i < n) ? vin[i] : 0u;
+    }
+    int      cur     = 0;
+    uint32_t skipped = 0;
+    const uint32_t my_first = warp * (32 * SMALL_KPT) + lane;
+    for (int p = 0; p < pt.num_passes; ++p) {
+        const DigitSpec ds = pt.d[p];
+        if (tid < RADIX)
+#pragma unroll
+            for (int w = 0; w < NW; ++w) tab[w * RADIX + tid] = 0u;
+        __syncthreads();  // table clean; previous scatter (or the load) visible
+        KeyT     key[SMALL_KPT];
+        uint32_t val[HAS_VALS ? SMALL_KPT : 1];
+        uint32_t uniform_rows = 0;
+#pragma unroll
+        for (int r = 0; r < SMALL_KPT; ++r) {
+            const uint32_t i = my_first + 32 * r;
+            key[r]           = kbuf[cur * SMALL_CAP + i];
+            if constexpr (HAS_VALS) val[r] = vbuf[cur * SMALL_CAP + i];
+            const uint32_t d = (i < n) ? digit_of(key[r], ds) : RADIX - 1;  // padding sits past n and ranks last
+            int all_same;
+            __match_all_sync(0xffffffffu, d, &all_same);
+            if (all_same) {
+                uniform_rows |= 1u << r;
+                if (lane == 0) atomicAdd(&gt[d], 32u);
+            } else {
+                atomicAdd(&gt[d], 1u);
+            }
+        }
+        __syncthreads();
+        uint32_t count = 0, incl = 0;
+        uint32_t pre[NW / 2];
+        if (tid < RADIX) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                if (w & 1) pre[w >> 1] |= count << 16; else pre[w >> 1] = count;
+                count += tab[w * RADIX + tid];
+            }
+            if (tid == RADIX - 1) count -= (SMALL_CAP - n);
+            hist[p * RADIX + tid] = count;
+            incl = count;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += x;
+            }
+            if (lane == 31) wsum[warp] = incl;
+        }
+        const int constant_digit = __syncthreads_or(tid < RADIX && count == n);  // also orders the wsum writes
+        if (allow_skip && constant_digit) {  // the pass is the identity
+            ++skipped;
+            if (tid == 0) plan->action[p] = PASS_NOTHING;
+            continue;
+        }
+        if (tid == 0) plan->action[p] = PASS_SORT;
+        if (tid < RADIX) {
+            uint32_t woff = 0;
+#pragma unroll
+            for (int w = 0; w < RADIX / 32; ++w) woff += (w < warp) ? wsum[w] : 0u;
+            const uint32_t local_base = woff + incl - count;
+#pragma unroll
+            for (int w = 0; w < NW; ++w)
+                tab[w * RADIX + tid] = local_base + ((w & 1) ? (pre[w >> 1] >> 16) : (pre[w >> 1] & 0xffffu));
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < SMALL_KPT; ++r) {
+            const uint32_t i = my_first + 32 * r;
+            const uint32_t d = (i < n) ? digit_of(key[r], ds) : RADIX - 1;
+            uint32_t pos;
+            if (uniform_rows & (1u << r)) {
+                uint32_t c = 0;
+                if (lane == 0) c = atoms_add_return(&gt[d], 32u);
+                pos = __shfl_sync(0xffffffffu, c, 0) + lane;
+            } else {
+                pos = atoms_add_return(&gt[d], 1u);  // same-word lanes are served in lane order (self-tested)
+            }
+            kbuf[(cur ^ 1) * SMALL_CAP + pos] = key[r];
+            if constexpr (HAS_VALS) vbuf[(cur ^ 1) * SMALL_CAP + pos] = val[r];
+        }
+        cur ^= 1;
+        __syncthreads();  // every warp is done with its table before the next pass re-zeroes all of them
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += SMALL_THREADS) {
+        out[i] = kbuf[cur * SMALL_CAP + i];
+        if constexpr (HAS_VALS) vout[i] = vbuf[cur * SMALL_CAP + i];
+    }
+    if (tid == 0) {
+        plan->num_skipped = skipped;
+        plan->num_copies  = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Self-test behind ATOMIC_RANK: for random digit patterns (1 .. 256 distinct values, single-bank and
 // spread layouts, partial warps) every lane does old = atomicAdd(&cnt[d], 1) and checks
 // old == count_before + (number of lower lanes with the same d).  Any violation disables the mode.

@@ -229,7 +229,18 @@ def distributed_sort(keys, ops, dist, key_type: str, scratch=None, group=None):
 
 def _distributed_sort_p2p(keys, ops, dist, key_type: str, s, group):
     """Same result as the NCCL path; the exchange is the fused gather + histogram kernel over peer memory."""
+    import os
+    import time
     import torch
+    timing = os.environ.get("RSB200_DIST_TIMING") == "1"   # developer switch: per-stage wall times (adds syncs)
+    marks = []
+
+    def mark(name):
+        if timing:
+            torch.cuda.synchronize()
+            marks.append((name, time.perf_counter()))
+
+    mark("start")
     world, rank = ops.p2p_world, ops.p2p_rank
     n_local = int(keys.numel())
     if n_local > ops.p2p_capacity:
@@ -238,8 +249,10 @@ def _distributed_sort_p2p(keys, ops, dist, key_type: str, s, group):
     # 1. local sort into the IPC-exported pair; `sel` says which of the two holds the sorted shard
     sel = ops.sorter.sort_device(ops.stream, keys.data_ptr(), ops.p2p_local[0], ops.p2p_local[1], n_local) if n_local else 0
     sorted_local = RawBuf(ops.p2p_local[sel], n_local, device=keys.device)
+    mark("local sort")
     # 2. exact splitters (all-reduces inside: every peer's local sort is complete once they return)
     cuts, _ = plan_exchange(sorted_local, ops, dist, key_type, group=group, device=keys.device)
+    mark("splitters")
     # 3. everybody learns everybody's cut positions and buffer selector
     mine = torch.from_numpy(np.concatenate((cuts, [sel])).astype(np.int64)).to(keys.device)
     parts = [torch.empty_like(mine) for _ in range(world)]
@@ -264,7 +277,11 @@ def _distributed_sort_p2p(keys, ops, dist, key_type: str, s, group):
         out = (other, gathered)[r][:n_recv]
     else:
         out = gathered[:0]
+    mark("exchange + final sort")
     # 5. nobody may overwrite its sorted shard (next local sort) before every rank has pulled from it
     done = torch.zeros(1, dtype=torch.int32, device=keys.device)
     dist.all_reduce(done, group=group)
+    mark("barrier")
+    if timing:
+        print(f"[rank {rank}] dist timing (ms): " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f}" for a, b in zip(marks, marks[1:])), flush=True)
     return out

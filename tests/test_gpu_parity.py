@@ -118,6 +118,32 @@ def test_ranking_modes_agree(rsb, gpu, oracle, t):
         assert np.array_equal(a, data[want]) and np.array_equal(b, a)
 
 
+@pytest.mark.parametrize("t", KEY_TYPES)
+def test_small_input_single_cta_path(rsb, gpu, oracle, t):
+    # n <= 4096 is sorted by one CTA in one launch; it must agree with the multi-kernel path bit for bit
+    ctx, st = gpu
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 31, 32, 33, 255, 256, 257, 1000, 4095, 4096):
+        for data in (oracle.dataset("uniform", t, n, SEED), oracle.dataset("inverted", t, n),
+                     rng.integers(0, 4, size=n).astype(numpy_dtype(t)), np.zeros(n, dtype=numpy_dtype(t))):
+            a, pa, ha = host_sort(rsb, gpu, data, t, with_perm=True)
+            b, pb, hb = host_sort(rsb, gpu, data, t, with_perm=True, flags=rsb.RS_NO_SMALL_PATH)
+            want = np.argsort(data, kind="stable").astype(np.uint32)
+            assert np.array_equal(pa, want) and np.array_equal(a, data[want]), (t, n)
+            assert np.array_equal(pb, want) and np.array_equal(b, a), (t, n)
+            assert np.array_equal(ha, hb), (t, n)
+    s = rsb.Sorter(ctx, t, 4096)
+    data = oracle.dataset("random", t, 3000)
+    l0 = s.launch_count
+    s.upload(st, data, None, 3000)
+    s.sort(st, 3000)
+    assert s.launch_count - l0 == 1
+    out = np.empty_like(data)
+    s.download(st, out, None, 3000)
+    assert np.array_equal(out, np.sort(data))
+    s.close()
+
+
 def test_empty_input(rsb, gpu):
     got, perm, _ = host_sort(rsb, gpu, np.empty(0, dtype=np.uint32), "u32", with_perm=True)
     assert got.size == 0 and perm.size == 0
