@@ -120,17 +120,17 @@ struct TileCfg;
 #endif
 #ifndef RS_U32VA_THREADS
 #define RS_U32VA_THREADS 512
-#define RS_U32VA_KPT 14
+#define RS_U32VA_KPT 15
 #define RS_U32VA_MINB 2
 #endif
 #ifndef RS_U64A_THREADS
 #define RS_U64A_THREADS 512
-#define RS_U64A_KPT 10
+#define RS_U64A_KPT 11
 #define RS_U64A_MINB 2
 #endif
 #ifndef RS_U64VA_THREADS
 #define RS_U64VA_THREADS 512
-#define RS_U64VA_KPT 8
+#define RS_U64VA_KPT 9
 #define RS_U64VA_MINB 2
 #endif
 template <> struct TileCfg<uint32_t, false, false> { static constexpr int THREADS = RS_U32_THREADS, KPT = RS_U32_KPT, MINB = RS_U32_MINB; };

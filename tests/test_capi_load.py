@@ -59,3 +59,18 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.lower().replace("oracle (", ""), os.path.join(dirpath, f)
+
+
+def test_bench_reference_arm_line():
+    # bench.py --impl reference: the reference's own CPU sort on a bounded sample, contract keys present
+    import json
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Gkeys/s" and line["higher_is_better"] is True
+    assert line["metric"] == "Gkeys/s sorting 2^28 uint32 keys" and 0 < line["value"] < 1.0
+    assert line["cpu_baseline"]["cores"] == 1 and line["cpu_baseline"]["kind"] in ("reference", "port")
+    assert line["e2e"] == {"value": line["value"], "unit": "Gkeys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -434,6 +434,20 @@ def test_full_size_2_28_other_types(rsb, gpu, t, kind):
     _full_size_case(rsb, gpu, t, kind, 1 << 28, with_perm=False)          # configs[3]
 
 
+def test_lookback_chunk_handover_exact(tmp_path):
+    # the >2^30-key path (a chunk's last tile hands the next chunk its base) checked EXACTLY at small sizes by shrinking
+    # the chunk to 3 tiles through the library's test hook; separate process because the hook is read once
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RSB200_DEBUG_TILES_PER_CHUNK="3")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "debug_chunks.py")], capture_output=True, text=True,
+                         env=env, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count(" OK ") == 24 and "FAIL" not in out.stdout, out.stdout[-2000:]
+
+
 def test_more_than_one_lookback_chunk(rsb, gpu):
     # > 2^30 keys: the look-back chain restarts at a chunk boundary with offsets from the chunk histograms
     _full_size_case(rsb, gpu, "u32", "uniform", (1 << 30) + 77777, with_perm=False)

@@ -6,7 +6,7 @@ from oracle import Oracle
 o = Oracle()
 ctx = rsb.Context(0); st = rsb.Stream(ctx)
 for t in ("u32","u64"):
-  for n in (8192*3, 8192*7+5, 100000, 1<<20):
+  for n in (11264*3, 11264*7+5, 100000, 1<<20):
     for kind in ("uniform","zeros","range"):
         data = o.dataset(kind, t, n)
         s = rsb.Sorter(ctx, t, n, rsb.RS_WITH_PERMUTATION)
