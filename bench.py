@@ -211,14 +211,15 @@ def bench_single(args):
     ctx.fill_dataset(st, KEY_TYPE, args.dataset, d_in.data_ptr(), n, seed=0x5EED)
     torch.cuda.synchronize()
     h_in.array[:] = d_in.cpu().numpy().view(np.uint32)   # same workload, now living in pinned host memory
-    # Two sorters on two streams: batch i+1 uploads while batch i sorts and downloads (PCIe is full duplex).
-    # Every step still moves its own 1 GiB in and 1 GiB out through the reference-facing calls.
-    e2e_steps = max(2, min(args.steps, 8))
-    lanes = [(rsb.Sorter(ctx, KEY_TYPE, n), rsb.Stream(ctx), rsb.HostBuffer(n, np.uint32)) for _ in range(2)]
+    # Three sorters on three streams: while batch i downloads, batch i+1 sorts and batch i+2 uploads (PCIe is full
+    # duplex).  Every step still moves its own 1 GiB in and 1 GiB out through the reference-facing calls.
+    NLANES = 3
+    e2e_steps = max(NLANES, min(args.steps, 9))
+    lanes = [(rsb.Sorter(ctx, KEY_TYPE, n), rsb.Stream(ctx), rsb.HostBuffer(n, np.uint32)) for _ in range(NLANES)]
 
     def e2e_run(steps):
         for i in range(steps):
-            srt, stream, hout = lanes[i & 1]
+            srt, stream, hout = lanes[i % NLANES]
             stream.sync()                       # the lane's previous batch (its host buffer) is complete
             srt.upload(stream, h_in, None, n)
             srt.sort(stream, n)
@@ -226,7 +227,7 @@ def bench_single(args):
         for _, stream, _ in lanes:
             stream.sync()
 
-    e2e_run(2)
+    e2e_run(NLANES)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e2e_run(e2e_steps)
@@ -245,8 +246,8 @@ def bench_single(args):
     seq_ms = (time.perf_counter() - t0) * 1e3
     e2e = {"value": n / e2e_ms / 1e6, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
            "h2d_bytes_per_step": n * KEY_BYTES, "d2h_bytes_per_step": n * KEY_BYTES,
-           "api": "rs_sorter_upload -> rs_sorter_sort -> rs_sorter_download_async on two sorters/streams "
-                  "(batch i+1 uploads while batch i downloads), pinned host buffers",
+           "api": "rs_sorter_upload -> rs_sorter_sort -> rs_sorter_download_async on three sorters/streams "
+                  "(batch i+2 uploads while batch i+1 sorts and batch i downloads), pinned host buffers",
            "timing": "host wall clock between device synchronisations",
            "single_batch_sequential_ms": seq_ms, "single_batch_sequential_gkeys_s": n / seq_ms / 1e6}
     for srt, stream, hout in lanes:
@@ -306,10 +307,24 @@ def bench_distributed(args):
     st = rsb.Stream(ctx, torch.cuda.current_stream().cuda_stream)
     ops = dsort.CudaOps(rsb, ctx, st, KEY_TYPE, n_local + n_local // 8 + (1 << 20))
     cap = n_local + n_local // 8 + (1 << 20)
-    if args.exchange == "p2p":
-        ops.enable_p2p(dist, cap)   # fused NVLink pull + histogram kernel instead of NCCL all-to-all
+    exchange = args.exchange
+    if exchange == "p2p":
+        # fused NVLink pull + histogram kernel instead of NCCL all-to-all; every rank must be able to map every peer
+        ok = 1
+        try:
+            ops.enable_p2p(dist, cap)
+        except Exception as e:  # noqa: BLE001  (CUDA IPC unavailable: fall back collectively, and say so in the line)
+            sys.stderr.write(f"[rank {rank}] peer mapping failed, falling back to NCCL all-to-all: {e}\n")
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if ok:
+                ops.close()
+                ops = dsort.CudaOps(rsb, ctx, st, KEY_TYPE, n_local + n_local // 8 + (1 << 20))
+            exchange = "nccl"
     shard = ops.empty(n_local)
-    scratch = {k: ops.empty(cap) for k in (("recv", "c") if args.exchange == "p2p" else ("a", "b", "recv", "c"))}
+    scratch = {k: ops.empty(cap) for k in (("recv", "c") if exchange == "p2p" else ("a", "b", "recv", "c"))}
     ctx.fill_dataset(st, KEY_TYPE, args.dataset, shard.data_ptr(), n_local, seed=0x5EED,
                      global_offset=rank * n_local, total_n=total)
     before = ctx.check(st, KEY_TYPE, shard.data_ptr(), n_local)
@@ -355,37 +370,40 @@ def bench_distributed(args):
     need = (n_local + cap) * KEY_BYTES * world          # pinned bytes over all ranks of this box
     e2e_ok = torch.tensor([1 if host_mem_available() > 3 * need else 0], dtype=torch.int64, device="cuda")
     dist.all_reduce(e2e_ok, op=dist.ReduceOp.MIN)
-    if int(e2e_ok.item()) == 0:
-        raise RuntimeError("bench: not enough host memory for the pinned end-to-end buffers")
-    h_in = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
-    h_out = torch.empty(cap, dtype=torch.int32, pin_memory=True)
-    h_in.copy_(shard)
-    d_shard = ops.empty(n_local)
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e = None
+    if int(e2e_ok.item()) == 1:
+        h_in = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
+        h_out = torch.empty(cap, dtype=torch.int32, pin_memory=True)
+        h_in.copy_(shard)
+        d_shard = ops.empty(n_local)
+        e2e_steps = max(1, min(args.steps, 2))
 
-    def e2e_once():
-        d_shard.copy_(h_in, non_blocking=True)
-        res = dsort.distributed_sort(d_shard, ops, dist, KEY_TYPE, scratch=scratch)
-        h_out[:res.numel()].copy_(res, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return res.numel()
+        def e2e_once():
+            d_shard.copy_(h_in, non_blocking=True)
+            res = dsort.distributed_sort(d_shard, ops, dist, KEY_TYPE, scratch=scratch)
+            h_out[:res.numel()].copy_(res, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return res.numel()
 
-    e2e_once()
-    dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(e2e_steps):
-        n_out = e2e_once()
-    e1.record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    t = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    e2e = {"value": total / e2e_ms / 1e6, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
-           "h2d_bytes_per_step": n_local * KEY_BYTES * world, "d2h_bytes_per_step": int(n_out) * KEY_BYTES * world,
-           "api": "pinned host shard -> H2D -> radix-sort_b200.dist.distributed_sort -> D2H, every rank"}
+        e2e_once()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(e2e_steps):
+            n_out = e2e_once()
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        e2e = {"value": total / e2e_ms / 1e6, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "h2d_bytes_per_step": n_local * KEY_BYTES * world, "d2h_bytes_per_step": int(n_out) * KEY_BYTES * world,
+               "api": "pinned host shard -> H2D -> radix-sort_b200.dist.distributed_sort -> D2H, every rank"}
+    else:
+        e2e = {"value": None, "unit": UNIT, "skipped": "not enough free host memory for the pinned shard buffers",
+               "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     out = dsort.distributed_sort(shard, ops, dist, KEY_TYPE, scratch=scratch)
     torch.cuda.synchronize()
 
@@ -417,7 +435,7 @@ def bench_distributed(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(world, args.dataset), "keys_total": total, "keys_per_gpu": n_local,
-                       "exchange": ("fused peer-memory pull + histogram kernel (CUDA IPC over NVLink)" if args.exchange == "p2p"
+                       "exchange": ("fused peer-memory pull + histogram kernel (CUDA IPC over NVLink)" if exchange == "p2p"
                                     else "NCCL all_to_all_single"),
                        "l2": "shards are GiBs, far larger than L2"},
             "clocks": clocks,
