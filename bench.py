@@ -308,6 +308,7 @@ def bench_distributed(args):
     ops = dsort.CudaOps(rsb, ctx, st, KEY_TYPE, n_local + n_local // 8 + (1 << 20))
     cap = n_local + n_local // 8 + (1 << 20)
     exchange = args.exchange
+    ops.final_step = args.final   # "merge": pairwise merge tree over peer memory, "sort": fused pull + histogram + onesweep passes
     if exchange == "p2p":
         # fused NVLink pull + histogram kernel instead of NCCL all-to-all; every rank must be able to map every peer
         ok = 1
@@ -435,8 +436,9 @@ def bench_distributed(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(world, args.dataset), "keys_total": total, "keys_per_gpu": n_local,
-                       "exchange": ("fused peer-memory pull + histogram kernel (CUDA IPC over NVLink)" if exchange == "p2p"
-                                    else "NCCL all_to_all_single"),
+                       "exchange": (("pairwise merge tree reading the peers' sorted runs over NVLink (CUDA IPC)" if args.final == "merge"
+                                     else "fused peer-memory pull + histogram kernel (CUDA IPC over NVLink) + final onesweep passes")
+                                    if exchange == "p2p" else "NCCL all_to_all_single + final local sort"),
                        "l2": "shards are GiBs, far larger than L2"},
             "clocks": clocks,
             "e2e": e2e, "gpu_launches": launches * world,
@@ -464,6 +466,9 @@ def main():
     ap.add_argument("--log2n", type=int, default=LOG2_SINGLE, help="single-GPU keys (default 28 = the contract workload)")
     ap.add_argument("--log2n-total", type=int, default=LOG2_DIST_TOTAL, help="multi-GPU total keys (default 33)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (developer runs)")
+    ap.add_argument("--final", default="merge", choices=["merge", "sort"],
+                    help="multi-GPU final local step with --exchange p2p: merge tree of the P received sorted runs (default) or a "
+                         "full local onesweep sort fed by the fused pull + histogram kernel")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU exchange: p2p = fused peer-memory pull + histogram kernel (default), nccl = all_to_all_single")
     args = ap.parse_args()

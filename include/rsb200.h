@@ -197,6 +197,14 @@ int rs_sorter_sort_segments_device(rs_sorter s, rs_stream st, int num_segments, 
                                    const uint64_t* seg_counts, int first_segment, void* d_gathered, void* d_keys_buf0,
                                    void* d_keys_buf1, int begin_bit, int end_bit, int* result_index);
 
+/* One level of pairwise merges of sorted key runs (the multi-GPU final step, SURVEY.md 8e.5: "or a P-way merge"):
+ * job j merges a[j] (a_counts[j] keys) and b[j] into out[j]; inputs may be peer memory (rs_ipc_open), so the first
+ * level is exchange and merge in one kernel.  d_splits: device scratch of splits_capacity uint64
+ * (>= sum over jobs of ceil((na+nb)/4096) + num_jobs).  Keys only; order is the key type's. */
+int rs_merge_runs_device(rs_context ctx, rs_stream st, rs_key_type type, int num_jobs, const void* const* d_a_ptrs,
+                         const uint64_t* a_counts, const void* const* d_b_ptrs, const uint64_t* b_counts,
+                         void* const* d_out_ptrs, uint64_t* d_splits, uint64_t splits_capacity);
+
 /* ---- device-side helpers used by the harness and the multi-GPU path ----------------------- */
 /* Fill d_out[0..n) with elements [global_offset, global_offset+n) of a dataset of total_n
  * elements (src/Dataset.h:84-137; the random kinds use a documented counter-based hash). */

@@ -107,6 +107,7 @@ def load_library():
         "rs_ipc_open": ([vp, C.c_char_p, C.POINTER(vp)], i),
         "rs_ipc_close": ([vp, vp], i),
         "rs_sorter_sort_segments_device": ([vp, vp, i, C.POINTER(vp), C.POINTER(u64), i, vp, vp, vp, i, i, C.POINTER(i)], i),
+        "rs_merge_runs_device": ([vp, vp, i, i, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), vp, u64], i),
         "rs_dataset_fill_device": ([vp, vp, i, i, u64, u64, u64, vp, u64], i),
         "rs_check_device": ([vp, vp, i, vp, u64, C.POINTER(u64 * 4)], i),
         "rs_check_permutation_device": ([vp, vp, i, vp, vp, vp, u64, C.POINTER(u64 * 2)], i),
@@ -196,6 +197,17 @@ class Context:
 
     def ipc_close(self, ptr: int):
         _check(self.lib.rs_ipc_close(self.handle, C.c_void_p(ptr)))
+
+    def merge_runs(self, stream, key_type, jobs, d_splits, splits_capacity):
+        """One level of pairwise merges: jobs = [(a_ptr, na, b_ptr, nb, out_ptr), ...] (<= 8), inputs may be peer memory."""
+        k = len(jobs)
+        ap = (C.c_void_p * k)(*[C.c_void_p(int(j[0])) for j in jobs])
+        an = (C.c_uint64 * k)(*[int(j[1]) for j in jobs])
+        bp = (C.c_void_p * k)(*[C.c_void_p(int(j[2])) for j in jobs])
+        bn = (C.c_uint64 * k)(*[int(j[3]) for j in jobs])
+        op = (C.c_void_p * k)(*[C.c_void_p(int(j[4])) for j in jobs])
+        _check(self.lib.rs_merge_runs_device(self.handle, stream.handle, KEY_TYPES[key_type], k, ap, an, bp, bn, op,
+                                             _addr(d_splits), splits_capacity))
 
     # -- device helpers -------------------------------------------------------------------------
     def fill_dataset(self, stream, key_type, kind, d_out, n, seed=0x5EED, global_offset=0, total_n=None):

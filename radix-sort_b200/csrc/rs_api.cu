@@ -7,6 +7,7 @@
 // kernel, the scan kernel and one onesweep kernel per 8-bit digit are enqueued back to back.
 #include "../../include/rsb200.h"
 #include "rs_kernels.cuh"
+#include "rs_merge.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -583,6 +584,43 @@ static int sort_segments_typed(rs_sorter s, rs_stream st, int num_segments, cons
                             nullptr, nullptr, nullptr, n, begin_bit, end_bit, profile, result_index, &seg);
 }
 
+template <typename KeyT>
+static int merge_runs_typed(rs_context ctx, cudaStream_t st, bool is_signed, int num_jobs, const void* const* a_ptrs,
+                            const uint64_t* a_counts, const void* const* b_ptrs, const uint64_t* b_counts, void* const* out_ptrs,
+                            uint64_t* d_splits, uint64_t splits_capacity) {
+    MergeBatch<KeyT> mb{};
+    mb.num_jobs = num_jobs;
+    mb.sign     = is_signed ? static_cast<KeyT>(static_cast<KeyT>(1) << (sizeof(KeyT) * 8 - 1)) : static_cast<KeyT>(0);
+    unsigned long long tiles = 0;
+    for (int j = 0; j < num_jobs; ++j) {
+        mb.a[j] = static_cast<const KeyT*>(a_ptrs[j]);
+        mb.b[j] = static_cast<const KeyT*>(b_ptrs[j]);
+        mb.out[j] = static_cast<KeyT*>(out_ptrs[j]);
+        mb.na[j] = a_counts[j];
+        mb.nb[j] = b_counts[j];
+        mb.tile_start[j] = tiles;
+        tiles += (a_counts[j] + b_counts[j] + MERGE_TILE - 1) / MERGE_TILE;
+    }
+    for (int j = num_jobs; j <= MERGE_MAX_JOBS; ++j) mb.tile_start[j] = tiles;
+    if (tiles == 0) return RS_OK;
+    if (tiles + num_jobs > splits_capacity) return fail(RS_CALCULATION_FAILED, "split scratch too small for this merge level");
+    if (tiles > 0x7fffffffull) return fail(RS_CALCULATION_FAILED, "too many merge tiles");
+    const unsigned long long boundaries = tiles + num_jobs;
+    const int pgrid = static_cast<int>(std::min<unsigned long long>((boundaries + 255) / 256, static_cast<unsigned long long>(ctx->sm_count) * 32));
+    rs_merge_partition_kernel<KeyT><<<pgrid, 256, 0, st>>>(mb, reinterpret_cast<unsigned long long*>(d_splits));
+    RS_CUDA(cudaGetLastError(), RS_CALCULATION_FAILED);
+    const size_t smem = sizeof(KeyT) * (MERGE_TILE + MERGE_TILE / 32);
+    auto kern = rs_merge_tiles_kernel<KeyT>;
+    static thread_local bool configured = false;
+    if (!configured) {
+        RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)), RS_CALCULATION_FAILED);
+        configured = true;
+    }
+    kern<<<static_cast<unsigned>(tiles), MERGE_THREADS, smem, st>>>(mb, reinterpret_cast<const unsigned long long*>(d_splits));
+    RS_CUDA(cudaGetLastError(), RS_CALCULATION_FAILED);
+    return RS_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
@@ -860,6 +898,20 @@ int rs_sorter_sort_segments_device(rs_sorter s, rs_stream st, int num_segments, 
                                              d_keys_buf0, d_keys_buf1, begin_bit, end_bit, profile, result_index);
     return sort_segments_typed<uint64_t>(s, st, num_segments, d_seg_ptrs, seg_counts, first_segment, d_gathered,
                                          d_keys_buf0, d_keys_buf1, begin_bit, end_bit, profile, result_index);
+}
+
+int rs_merge_runs_device(rs_context ctx, rs_stream st, rs_key_type type, int num_jobs, const void* const* d_a_ptrs,
+                         const uint64_t* a_counts, const void* const* d_b_ptrs, const uint64_t* b_counts,
+                         void* const* d_out_ptrs, uint64_t* d_splits, uint64_t splits_capacity) {
+    if (!ctx || !st || !d_a_ptrs || !a_counts || !d_b_ptrs || !b_counts || !d_out_ptrs || !d_splits)
+        return fail(RS_CALCULATION_FAILED, "null argument");
+    if (num_jobs < 1 || num_jobs > MERGE_MAX_JOBS) return fail(RS_CALCULATION_FAILED, "1..8 merge jobs per call");
+    if (type < RS_KEY_U32 || type > RS_KEY_I64) return fail(RS_CALCULATION_FAILED, "unknown key type");
+    RS_CUDA(cudaSetDevice(ctx->device), RS_CALCULATION_FAILED);
+    const bool sg = (type == RS_KEY_I32 || type == RS_KEY_I64);
+    if (type == RS_KEY_U32 || type == RS_KEY_I32)
+        return merge_runs_typed<uint32_t>(ctx, st->st, sg, num_jobs, d_a_ptrs, a_counts, d_b_ptrs, b_counts, d_out_ptrs, d_splits, splits_capacity);
+    return merge_runs_typed<uint64_t>(ctx, st->st, sg, num_jobs, d_a_ptrs, a_counts, d_b_ptrs, b_counts, d_out_ptrs, d_splits, splits_capacity);
 }
 
 int rs_device_alloc(rs_context ctx, size_t bytes, void** out) {

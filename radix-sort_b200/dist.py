@@ -270,13 +270,17 @@ def _distributed_sort_p2p(keys, ops, dist, key_type: str, s, group):
         return t if (t is not None and t.numel() >= n) else ops.empty(max(n, 1))
 
     gathered, other = buf("recv", n_recv), buf("c", n_recv)
-    # 4. fused exchange + final sort: pull my segments from every peer over NVLink while counting digits
-    if n_recv:
+    if n_recv == 0:
+        out = gathered[:0]
+    elif getattr(ops, "final_step", "merge") == "merge" and (world & (world - 1)) == 0:
+        # 4a. final step as a merge tree: my P segments are sorted runs; level 1 merges pairs of them
+        #     straight out of the peers' memory (exchange + merge in one kernel), later levels are local
+        out = _merge_tree(ops, key_type, ptrs, counts, gathered, other, n_recv, kb, s)
+    else:
+        # 4b. fused exchange + histogram, then the onesweep passes of a final local sort
         r = ops.sorter.sort_segments_device(ops.stream, ptrs, counts, rank, gathered.data_ptr(), other.data_ptr(),
                                             gathered.data_ptr())
         out = (other, gathered)[r][:n_recv]
-    else:
-        out = gathered[:0]
     mark("exchange + final sort")
     # 5. nobody may overwrite its sorted shard (next local sort) before every rank has pulled from it
     done = torch.zeros(1, dtype=torch.int32, device=keys.device)
@@ -285,3 +289,37 @@ def _distributed_sort_p2p(keys, ops, dist, key_type: str, s, group):
     if timing:
         print(f"[rank {rank}] dist timing (ms): " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f}" for a, b in zip(marks, marks[1:])), flush=True)
     return out
+
+
+def _merge_tree(ops, key_type, ptrs, counts, buf_x, buf_y, n_total, kb, scratch):
+    """Merge the sorted runs (ptr, count) pairwise, level by level, ping-ponging between buf_x and buf_y."""
+    import torch
+    tiles_max = (n_total + 4095) // 4096 + 2 * len(ptrs) + 16
+    splits = scratch.get("splits")
+    if splits is None or splits.numel() < tiles_max:
+        splits = torch.empty(tiles_max, dtype=torch.int64, device=buf_x.device)
+        scratch["splits"] = splits
+    runs = [(int(p), int(c)) for p, c in zip(ptrs, counts)]
+    bufs = [buf_x, buf_y]
+    level = 0
+    if len(runs) == 1:  # single rank: the run is already the result; bring it into local memory through a 1-job merge
+        runs.append((runs[0][0], 0))
+    while len(runs) > 1:
+        dst = bufs[level & 1]
+        jobs, nxt, off = [], [], 0
+        for i in range(0, len(runs) - 1, 2):
+            (pa, na), (pb, nb) = runs[i], runs[i + 1]
+            out_ptr = dst.data_ptr() + off * kb
+            jobs.append((pa, na, pb, nb, out_ptr))
+            nxt.append((out_ptr, na + nb))
+            off += na + nb
+        if len(runs) & 1:
+            nxt.append(runs[-1])  # odd run out: joins the next level (it may still live in peer memory)
+        for lo in range(0, len(jobs), 8):
+            ops.ctx.merge_runs(ops.stream, key_type, jobs[lo:lo + 8], splits.data_ptr(), splits.numel())
+        runs = nxt
+        level += 1
+    final_ptr, final_n = runs[0]
+    dst = bufs[(level - 1) & 1]
+    assert final_ptr == dst.data_ptr() and final_n == n_total
+    return dst[:n_total]

@@ -383,6 +383,35 @@ def test_fused_gather_sort_of_segments(rsb, gpu, oracle, t):
     s.close()
 
 
+@pytest.mark.parametrize("t", KEY_TYPES)
+def test_merge_runs(rsb, gpu, oracle, t):
+    # pairwise merge of sorted runs (multi-GPU final step), all runs local here: ragged, empty, several jobs per call
+    torch = _torch()
+    ctx, st = gpu
+    dt = numpy_dtype(t)
+    kb = dt.itemsize
+    rng = np.random.default_rng(3)
+    sizes = [(0, 0), (1, 0), (0, 5), (1, 1), (4096, 4096), (4095, 4097), (100003, 7), (250000, 333333), (5, 60001)]
+    runs = []
+    for na, nb in sizes:
+        a = np.sort(oracle.dataset("uniform", t, na + 1, SEED + na)[:na]) if na else np.empty(0, dt)
+        b = np.sort(rng.integers(-50, 50, size=nb).astype(dt)) if nb else np.empty(0, dt)  # duplicates, negatives for signed
+        runs.append((a, b))
+    splits = torch.empty(1 << 16, dtype=torch.int64, device="cuda")
+    for lo in range(0, len(runs), 4):  # up to 8 jobs per call; use 4 here
+        batch = runs[lo:lo + 4]
+        d_a = [_dev(a) if len(a) else torch.empty(1, dtype=torch.int32 if kb == 4 else torch.int64, device="cuda") for a, _ in batch]
+        d_b = [_dev(b) if len(b) else torch.empty(1, dtype=torch.int32 if kb == 4 else torch.int64, device="cuda") for _, b in batch]
+        d_o = [torch.empty(max(1, len(a) + len(b)), dtype=d_a[0].dtype, device="cuda") for a, b in batch]
+        torch.cuda.synchronize()
+        ctx.merge_runs(st, t, [(d_a[i].data_ptr(), len(batch[i][0]), d_b[i].data_ptr(), len(batch[i][1]), d_o[i].data_ptr())
+                               for i in range(len(batch))], splits.data_ptr(), splits.numel())
+        st.sync()
+        for i, (a, b) in enumerate(batch):
+            got = _host(d_o[i], dt)[:len(a) + len(b)]
+            assert np.array_equal(got, np.sort(np.concatenate((a, b)))), (t, len(a), len(b))
+
+
 # ---- BASELINE.json full sizes: size-independent properties, everything resident on the device -------
 
 def _full_size_case(rsb, gpu, t, kind, n, with_perm):

@@ -29,6 +29,7 @@ def main():
         np_dt = rsb.key_dtype(key_type)
         n_local = total // world + (17 * rank if key_type == "i32" else 0)  # ragged shards for one type
         ops = dsort.CudaOps(rsb, ctx, st, key_type, 2 * n_local + 4096)
+        ops.final_step = args.get("final", "merge")
         if mode == "p2p":
             ops.enable_p2p(dist, 2 * n_local + 4096)
         for kind in ("uniform", "random", "range", "inverted", "zeros"):
@@ -53,7 +54,7 @@ def main():
                 n_all = len(ins)
                 ok = np.array_equal(outs, np.sort(ins))
                 bal = all(int(sizes[r, 1]) == ((r + 1) * n_all) // world - (r * n_all) // world for r in range(world))
-                print(f"[{mode}] {key_type} {kind:9s} total={n_all} world={world}: {'OK' if ok and bal else 'FAIL'} sizes={sizes[:, 1].tolist()}",
+                print(f"[{mode}/{ops.final_step}] {key_type} {kind:9s} total={n_all} world={world}: {'OK' if ok and bal else 'FAIL'} sizes={sizes[:, 1].tolist()}",
                       flush=True)
                 failures += int(not (ok and bal))
         ops.close()
