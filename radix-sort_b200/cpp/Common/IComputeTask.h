@@ -1,5 +1,6 @@
-// IComputeTask.h -- the five-call task contract of the reference (Common/IComputeTask.h:12-35), with the
-// OpenCL handle types replaced by the CUDA-side wrappers of ComputeState.h.
+// IComputeTask.h -- the task contract the reference's test runner drives (Common/IComputeTask.h:12-35):
+// the same five virtuals in the same order of use; cl::Device / cl::Context / cl::CommandQueue are
+// rs::Device / rs::Context / rs::Stream (Common/ComputeState.h).
 #pragma once
 #include "CommonDefs.h"
 #include "ComputeState.h"
@@ -7,14 +8,15 @@
 class IComputeTask {
 public:
     virtual ~IComputeTask() = default;
-    /// Allocate everything the task needs on the device.
+
+    /// 1. device-side allocation; false aborts the run
     virtual bool InitResources(rs::Device Device, rs::Context Context) = 0;
-    /// Undo InitResources.
-    virtual void ReleaseResources() = 0;
-    /// Run (and time) the GPU path.
-    virtual void ComputeGPU(rs::Context Context, rs::Stream CommandQueue, const LocalWorkSize& LocalWorkSize) = 0;
-    /// Produce the golden result on the host.
+    /// 2. golden result on the host (std::sort, CPU radix sort)
     virtual void ComputeCPU() = 0;
-    /// GPU result == golden result?
+    /// 3. the GPU path, warm run + timed runs; LocalWorkSize is accepted and ignored
+    virtual void ComputeGPU(rs::Context Context, rs::Stream CommandQueue, const LocalWorkSize& LocalWorkSize) = 0;
+    /// 4. GPU result against the golden result
     virtual bool ValidateResults() = 0;
+    /// 5. undo InitResources
+    virtual void ReleaseResources() = 0;
 };

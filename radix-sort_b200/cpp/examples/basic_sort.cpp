@@ -1,6 +1,6 @@
-// basic_sort -- the documented library-user sequence of the reference (examples/basic_sort/basic_sort.cpp:24-139)
-// against the B200 facade: Resize -> HostSpans -> initialize -> padGPUData -> uploadData -> calculate ->
-// downloadData -> compare with std::sort -> getRuntimes -> release.
+// basic_sort -- what a library user writes (counterpart of the reference's examples/basic_sort/basic_sort.cpp):
+// size the host buffers with Resize(), wrap them in HostSpans, initialize -> padGPUData -> uploadData -> calculate ->
+// downloadData, compare with std::sort, print getRuntimes(), release.
 //   usage: basic_sort [num_elements=1048576]
 #include "Common/ComputeState.h"
 #include "Dataset.h"
@@ -9,57 +9,63 @@
 #include <algorithm>
 #include <cstdlib>
 #include <iostream>
+#include <limits>
 #include <numeric>
 #include <vector>
 
+namespace {
+
 template <typename T>
-static bool sortAndVerify(ComputeState& compute, uint64_t numElements) {
+bool run_one(ComputeState& gpu, uint64_t n) {
     using P = AlgorithmParameters<T>;
-    RandomDistributed<T> dataset(numElements);
-    RadixSortGPU<T>      sorter;
-    const uint64_t       rounded = sorter.Resize(numElements);
+    const RandomDistributed<T> input(n);
+    RadixSortGPU<T>            sorter;
+    const uint64_t             padded = sorter.Resize(n);  // next multiple of 1024, as callers of the reference do
 
-    std::vector<T>        hKeys(rounded), hResult(rounded);
-    std::vector<uint32_t> hHistograms(P::_HISTOSIZE), hGlobsum(P::_NUM_HISTOSPLIT), hPermut(rounded);
-    std::copy_n(dataset.dataset.begin(), numElements, hKeys.begin());
-    // keys past numElements must sort to the end.  The host tail is what uploadData ships (it overwrites the
-    // device-side padGPUData fill, as in the reference), so fill it with max: padGPUData's max-1 would sort
-    // in front of a genuine max key, and RandomDistributed always contains one.
-    std::fill(hKeys.begin() + numElements, hKeys.end(), std::numeric_limits<T>::max());
-    std::iota(hPermut.begin(), hPermut.end(), 0U);
-    HostSpans<T> spans{{hKeys.data(), hKeys.size()}, {hHistograms.data(), hHistograms.size()},
-                       {hGlobsum.data(), hGlobsum.size()}, {hPermut.data(), hPermut.size()},
-                       {hResult.data(), hResult.size()}};
+    // host side: keys (+ tail), result, the two auxiliary read-backs and the index payload
+    std::vector<T>        keys(padded, std::numeric_limits<T>::max()), sorted(padded);
+    std::vector<uint32_t> histograms(P::_HISTOSIZE), globsum(P::_NUM_HISTOSPLIT), permutation(padded);
+    std::copy(input.dataset.begin(), input.dataset.end(), keys.begin());
+    // The tail past n is max, not padGPUData's max-1: uploadData ships the host tail over the device-side fill (as in
+    // the reference), and max-1 would sort in front of the genuine max key every RandomDistributed set contains.
+    std::iota(permutation.begin(), permutation.end(), 0U);
 
-    if (sorter.initialize(compute.device(), compute.m_CLContext, numElements, spans) != OperationStatus::OK) {
-        std::cerr << "Failed to initialize RadixSortGPU: " << rs_last_error_string() << "\n";
+    const HostSpans<T> spans{{keys.data(), keys.size()},
+                             {histograms.data(), histograms.size()},
+                             {globsum.data(), globsum.size()},
+                             {permutation.data(), permutation.size()},
+                             {sorted.data(), sorted.size()}};
+    auto ok = [](OperationStatus s, const char* what) {
+        if (s == OperationStatus::OK) return true;
+        std::cerr << what << " failed: " << rs_status_string(static_cast<int>(s)) << " (" << rs_last_error_string() << ")\n";
         return false;
-    }
+    };
+    auto& queue = gpu.m_CLCommandQueue;
+    if (!ok(sorter.initialize(gpu.device(), gpu.m_CLContext, n, spans), "initialize")) return false;
     sorter.setLogStream(&std::cout);
-    auto& queue = compute.m_CLCommandQueue;
-    if (rounded != numElements) sorter.padGPUData(queue, sizeof(T) * numElements);
-    if (sorter.uploadData(queue) != OperationStatus::OK) { std::cerr << "Upload failed\n"; return false; }
-    if (sorter.calculate(queue) != OperationStatus::OK) { std::cerr << "GPU sort failed\n"; return false; }
-    if (sorter.downloadData(queue) != OperationStatus::OK) { std::cerr << "Download failed\n"; return false; }
+    if (padded != n) sorter.padGPUData(queue, sizeof(T) * n);
+    if (!ok(sorter.uploadData(queue), "uploadData") || !ok(sorter.calculate(queue), "calculate") ||
+        !ok(sorter.downloadData(queue), "downloadData"))
+        return false;
 
-    std::vector<T> reference(dataset.dataset.begin(), dataset.dataset.begin() + numElements);
-    std::sort(reference.begin(), reference.end());
-    const bool correct = std::equal(reference.begin(), reference.end(), hResult.begin());
+    std::vector<T> expected(input.dataset);
+    std::sort(expected.begin(), expected.end());
+    const bool same = std::equal(expected.begin(), expected.end(), sorted.begin());
 
-    const auto rt = sorter.getRuntimes();
-    std::cout << "\n--- Timing (avg ms, CUDA events) ---\n"
-              << "  Histogram : " << rt.timeHisto.avg << "\n  Scan      : " << rt.timeScan.avg
-              << "\n  Reorder   : " << rt.timeReorder.avg << "\n  Paste     : " << rt.timePaste.avg
-              << "\n  Total     : " << rt.timeTotal.avg << "\n";
+    const RuntimesGPU rt = sorter.getRuntimes();
+    std::cout << "avg ms (CUDA events): histogram " << rt.timeHisto.avg << ", scan " << rt.timeScan.avg << ", reorder "
+              << rt.timeReorder.avg << ", paste " << rt.timePaste.avg << ", total " << rt.timeTotal.avg << "\n";
     sorter.release();
-    return correct;
+    return same;
 }
+
+}  // namespace
 
 int main(int argc, char** argv) {
     const uint64_t n = argc > 1 ? std::strtoull(argv[1], nullptr, 10) : (1ULL << 20);
-    ComputeState   compute;
-    if (!compute.init()) return 2;
-    const bool ok = sortAndVerify<uint32_t>(compute, n) && sortAndVerify<int64_t>(compute, n);
+    ComputeState   gpu;
+    if (!gpu.init()) return 2;
+    const bool ok = run_one<uint32_t>(gpu, n) && run_one<int64_t>(gpu, n);
     std::cout << (ok ? "Sort verified: results match std::sort\n" : "MISMATCH against std::sort\n");
     return ok ? 0 : 1;
 }

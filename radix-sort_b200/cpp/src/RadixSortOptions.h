@@ -1,34 +1,41 @@
-// RadixSortOptions.h -- runtime flags of the task (reference src/RadixSortOptions.h:8-40): same flag
-// spellings and defaults, parsed from a vector of strings.
+// RadixSortOptions.h -- runtime switches of the task, same names and command-line spellings as the
+// reference's RadixSortOptions (src/RadixSortOptions.h:8-40); parsing is table-driven here.
 #pragma once
 #include "Parameters.h"
 
+#include <array>
 #include <cstddef>
 #include <string>
+#include <string_view>
+#include <utility>
 #include <vector>
 
 struct RadixSortOptions {
-    std::size_t num_elements{AlgorithmParameters<float>::Reference::_NUM_MAX_INPUT_ELEMS};  // 2^25, as the reference
-    bool        perf_to_stdout{false};
-    bool        perf_to_csv{false};
-    bool        perf_csv_to_stdout{false};
-    bool        verbose{false};
+    /// keys to sort; the reference's default is its 2^25 maximum
+    std::size_t num_elements = AlgorithmParameters<float>::Reference::_NUM_MAX_INPUT_ELEMS;
+    bool perf_to_stdout     = false;  ///< --perf-to-stdout      human-readable timing table
+    bool perf_to_csv        = false;  ///< --perf-to-csv         append to radix_HH-MM-SS.csv
+    bool perf_csv_to_stdout = false;  ///< --perf-csv-to-stdout  CSV rows on stdout
+    bool verbose            = false;  ///< -v | --verbose
 
     RadixSortOptions() = default;
+
     explicit RadixSortOptions(const std::vector<std::string>& args) {
-        for (std::size_t i = 0; i < args.size(); ++i) {
-            const std::string& a = args[i];
-            if (a == "--num-elements" && i + 1 < args.size()) {
-                num_elements = static_cast<std::size_t>(std::stoull(args[++i]));  // reference: std::stoi, N < 2^31
-            } else if (a == "--perf-to-stdout") {
-                perf_to_stdout = true;
-            } else if (a == "--perf-to-csv") {
-                perf_to_csv = true;
-            } else if (a == "--perf-csv-to-stdout") {
-                perf_csv_to_stdout = true;
-            } else if (a == "-v" || a == "--verbose") {
-                verbose = true;
+        const std::array<std::pair<std::string_view, bool RadixSortOptions::*>, 5> switches{{
+            {"--perf-to-stdout", &RadixSortOptions::perf_to_stdout},
+            {"--perf-to-csv", &RadixSortOptions::perf_to_csv},
+            {"--perf-csv-to-stdout", &RadixSortOptions::perf_csv_to_stdout},
+            {"--verbose", &RadixSortOptions::verbose},
+            {"-v", &RadixSortOptions::verbose},
+        }};
+        for (auto it = args.begin(); it != args.end(); ++it) {
+            if (*it == "--num-elements") {
+                if (++it == args.end()) break;  // the reference reads past the end here; we stop
+                num_elements = static_cast<std::size_t>(std::stoull(*it));  // 64-bit: no 2^31 limit of std::stoi
+                continue;
             }
+            for (const auto& [name, member] : switches)
+                if (*it == name) this->*member = true;
         }
     }
 };
