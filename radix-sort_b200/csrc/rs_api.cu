@@ -609,6 +609,24 @@ static int merge_runs_typed(rs_context ctx, cudaStream_t st, bool is_signed, int
     const int pgrid = static_cast<int>(std::min<unsigned long long>((boundaries + 255) / 256, static_cast<unsigned long long>(ctx->sm_count) * 32));
     rs_merge_partition_kernel<KeyT><<<pgrid, 256, 0, st>>>(mb, reinterpret_cast<unsigned long long*>(d_splits));
     RS_CUDA(cudaGetLastError(), RS_CALCULATION_FAILED);
+    static const bool one_tile_per_cta = std::getenv("RSB200_MERGE_UNPIPELINED") != nullptr;  // A/B switch for profiling
+    if (!one_tile_per_cta) {
+        unsigned long long max_tiles = 0;
+        for (int j = 0; j < num_jobs; ++j) max_tiles = std::max(max_tiles, mb.tile_start[j + 1] - mb.tile_start[j]);
+        if (max_tiles * num_jobs > 0xffffffffull) return fail(RS_CALCULATION_FAILED, "too many merge tiles");
+        const size_t smem = sizeof(KeyT) * (2 * MERGE_TILE + 4 * (MERGE_LINE_BYTES / sizeof(KeyT)) + MERGE_TILE / 32);
+        auto kern = rs_merge_tiles_pipelined_kernel<KeyT>;
+        static thread_local int ctas_per_sm = 0;
+        if (!ctas_per_sm) {
+            RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)), RS_CALCULATION_FAILED);
+            RS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, MERGE_THREADS, smem), RS_CALCULATION_FAILED);
+            if (ctas_per_sm < 1) return fail(RS_CALCULATION_FAILED, "merge kernel does not fit on an SM");
+        }
+        const unsigned grid = static_cast<unsigned>(std::min<unsigned long long>(tiles, static_cast<unsigned long long>(ctx->sm_count) * ctas_per_sm));
+        kern<<<grid, MERGE_THREADS, smem, st>>>(mb, reinterpret_cast<const unsigned long long*>(d_splits), static_cast<uint32_t>(max_tiles));
+        RS_CUDA(cudaGetLastError(), RS_CALCULATION_FAILED);
+        return RS_OK;
+    }
     const size_t smem = sizeof(KeyT) * (MERGE_TILE + MERGE_TILE / 32);
     auto kern = rs_merge_tiles_kernel<KeyT>;
     static thread_local bool configured = false;

@@ -131,4 +131,168 @@ rs_merge_tiles_kernel(const MergeBatch<KeyT> mb, const unsigned long long* __res
     for (uint32_t i = tid; i < n_out; i += MERGE_THREADS) dst[i] = sk[merge_pad(i)];
 }
 
+
+// ---- persistent, software-pipelined variant (default) ------------------------------------------------------
+// One CTA walks a strided sequence of tiles.  While it merges tile i out of shared memory, the loads of tile i+1
+// are already in flight into registers and the two split words of tile i+2 are on their way, so a peer load's
+// ~1-2 us NVLink round trip is hidden behind a whole merge phase per CTA.  The sequence interleaves the jobs of the
+// batch (slot s -> job s % J, tile s / J): at level 1 of the tree every job reads two different source GPUs, so all
+// P sources are read at the same rate all the time instead of every GPU pulling from GPU 0 and 1 first.
+//
+// Peer loads must be line-aligned per warp: a warp request that straddles 128-byte lines runs at ~430 GB/s over
+// NVLink instead of ~790 (tools/peerbw.cu).  The pieces of a tile start at arbitrary elements, so the tile is loaded
+// WHOLE LINES at a time with 16-byte loads into a "virtual" layout that is kept in shared memory as it is:
+//     [ off_a slack | la elements of A | slack up to span_a ]  [ off_b slack | lb elements of B | slack up to span_b ]
+// span_a / span_b are multiples of the line, so both pieces start line-aligned in global AND in shared memory; the
+// merge simply reads A at sk + off_a and B at sk + span_a + off_b.  Only lines that hold at least one element of
+// the piece are touched, so no load leaves the caller's allocation granule.
+constexpr int MERGE_LINE_BYTES = 128;
+
+template <typename KeyT>
+struct MergeSlot {          // per thread
+    const uint4*       pa;     // row-0 vector of this thread in A's lines
+    const uint4*       pb;     // row-0 vector of this thread in B's lines (biased by -span_a)
+    KeyT*              out;    // first output element of the tile
+    uint32_t           la, lb;
+    uint32_t           off_a;  // A starts at sk[off_a]
+    uint32_t           span_a; // elements of shared memory taken by A's lines
+    uint32_t           org_b;  // B starts at sk[org_b] (= span_a + off_b)
+    uint32_t           total;  // span_a + span_b
+};
+
+template <typename KeyT>
+__global__ void __launch_bounds__(MERGE_THREADS, 4)
+rs_merge_tiles_pipelined_kernel(const MergeBatch<KeyT> mb_param, const unsigned long long* __restrict__ splits,
+                                const uint32_t max_tiles_per_job) {
+    constexpr uint32_t LINE = MERGE_LINE_BYTES / sizeof(KeyT);          // elements per line
+    constexpr uint32_t VEC  = 16 / sizeof(KeyT);                        // elements per 16-byte load
+    constexpr uint32_t SK   = MERGE_TILE + 4 * LINE;                    // staged inputs incl. alignment slack
+    constexpr int      ROWS = (MERGE_TILE + 3 * LINE + VEC * MERGE_THREADS - 1) / (VEC * MERGE_THREADS);
+    extern __shared__ __align__(16) unsigned char merge_smem[];
+    __shared__ MergeBatch<KeyT> mb;
+    KeyT* const sk = reinterpret_cast<KeyT*>(merge_smem);   // [SK]                          virtual layout, see above
+    KeyT* const so = sk + SK;                               // [MERGE_TILE + MERGE_TILE/32]  transposed outputs
+    const int tid = threadIdx.x;
+    if (tid == 0) mb = mb_param;
+    __syncthreads();
+    const uint32_t J = static_cast<uint32_t>(mb.num_jobs);
+    const uint32_t S = J * max_tiles_per_job;               // sequence slots (host guarantees < 2^32)
+    const KeyT     sign = mb.sign;
+
+    // next slot >= s (stepping by the grid) that names an existing tile; S if none
+    auto seek = [&](uint32_t s) {
+        while (s < S) {
+            const uint32_t job = s % J, lt = s / J;
+            if (lt < static_cast<uint32_t>(mb.tile_start[job + 1] - mb.tile_start[job])) break;
+            if (S - s <= gridDim.x) { s = S; break; }
+            s += gridDim.x;
+        }
+        return s;
+    };
+    auto advance = [&](uint32_t s) { return (S - s <= gridDim.x) ? S : seek(s + gridDim.x); };
+    // the two split words of slot s
+    auto load_splits = [&](uint32_t s, unsigned long long& s0, unsigned long long& s1) {
+        const uint32_t job = s % J, lt = s / J;
+        const unsigned long long g = mb.tile_start[job] + lt + job;
+        s0 = splits[g]; s1 = splits[g + 1];
+    };
+    auto make_slot = [&](uint32_t s, unsigned long long a0, unsigned long long a1) {
+        const uint32_t job = s % J, lt = s / J;
+        const unsigned long long total = mb.na[job] + mb.nb[job];
+        const unsigned long long d0 = static_cast<unsigned long long>(lt) * MERGE_TILE;
+        const unsigned long long d1 = (d0 + MERGE_TILE < total) ? d0 + MERGE_TILE : total;
+        MergeSlot<KeyT> t;
+        const KeyT* const a = mb.a[job] + a0;
+        const KeyT* const b = mb.b[job] + (d0 - a0);
+        t.out = mb.out[job] + d0;
+        t.la = static_cast<uint32_t>(a1 - a0); t.lb = static_cast<uint32_t>((d1 - a1) - (d0 - a0));
+        t.off_a = t.la ? static_cast<uint32_t>(reinterpret_cast<uintptr_t>(a) / sizeof(KeyT)) & (LINE - 1) : 0;
+        const uint32_t off_b = t.lb ? static_cast<uint32_t>(reinterpret_cast<uintptr_t>(b) / sizeof(KeyT)) & (LINE - 1) : 0;
+        t.span_a = (t.off_a + t.la + LINE - 1) & ~(LINE - 1);
+        t.org_b  = t.span_a + off_b;
+        t.total  = t.span_a + ((off_b + t.lb + LINE - 1) & ~(LINE - 1));
+        t.pa = reinterpret_cast<const uint4*>(a - t.off_a) + tid;
+        t.pb = reinterpret_cast<const uint4*>(b - off_b - t.span_a) + tid;   // never dereferenced below span_a
+        return t;
+    };
+    uint4 nx[ROWS];
+    auto issue_loads = [&](const MergeSlot<KeyT>& t) {
+#pragma unroll
+        for (int k = 0; k < ROWS; ++k) {
+            const uint32_t v = (tid + k * MERGE_THREADS) * VEC;     // virtual element index of this vector
+            const uint4*   p = (v < t.span_a ? t.pa : t.pb) + k * MERGE_THREADS;
+            if (v < t.total) nx[k] = *p;
+        }
+    };
+
+    uint32_t s_cur = seek(blockIdx.x);
+    if (s_cur >= S) return;
+    unsigned long long p0, p1;
+    load_splits(s_cur, p0, p1);
+    MergeSlot<KeyT> cur = make_slot(s_cur, p0, p1);
+    issue_loads(cur);
+    uint32_t s_nxt = advance(s_cur);
+    if (s_nxt < S) load_splits(s_nxt, p0, p1);
+    KeyT sign4[VEC];
+#pragma unroll
+    for (uint32_t i = 0; i < VEC; ++i) sign4[i] = sign;
+    const uint4 signv = *reinterpret_cast<const uint4*>(sign4);
+
+    while (true) {
+        // stage tile `cur` (its loads were issued one iteration ago), keys mapped to unsigned order
+        const uint32_t la = cur.la, lb = cur.lb, n_out = la + lb;
+        const KeyT* const sa = sk + cur.off_a;
+        const KeyT* const sb = sk + cur.org_b;
+#pragma unroll
+        for (int k = 0; k < ROWS; ++k) {
+            const uint32_t c = tid + k * MERGE_THREADS;
+            if (c * VEC < cur.total)
+                reinterpret_cast<uint4*>(sk)[c] = make_uint4(nx[k].x ^ signv.x, nx[k].y ^ signv.y, nx[k].z ^ signv.z, nx[k].w ^ signv.w);
+        }
+        KeyT* const dst = cur.out;
+        __syncthreads();
+        // put tile i+1 in flight, ask for the splits of tile i+2
+        const bool more = s_nxt < S;
+        if (more) {
+            cur = make_slot(s_nxt, p0, p1);
+            issue_loads(cur);
+            s_nxt = advance(s_nxt);
+            if (s_nxt < S) load_splits(s_nxt, p0, p1);
+        }
+        // merge tile i out of shared memory; reads past the end of a piece hit the slack (or the other piece) and
+        // are never selected -- the index tests in take_a decide
+        uint32_t diag = tid * MERGE_ITEMS;
+        if (diag > n_out) diag = n_out;
+        uint32_t ai;
+        {
+            uint32_t lo = diag > lb ? diag - lb : 0, hi = diag < la ? diag : la;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (sa[mid] <= sb[diag - 1 - mid]) lo = mid + 1; else hi = mid;
+            }
+            ai = lo;
+        }
+        uint32_t bi = diag - ai;
+        KeyT     ka = sa[ai], kb = sb[bi];
+        KeyT* const wo = so + tid * MERGE_ITEMS + (tid >> 1);      // == merge_pad(tid * MERGE_ITEMS + k) - k
+#pragma unroll
+        for (int k = 0; k < MERGE_ITEMS; ++k) {
+            const bool take_a = (bi >= lb) || (ai < la && ka <= kb);
+            wo[k] = take_a ? ka : kb;
+            if (take_a) ka = sa[++ai]; else kb = sb[++bi];
+        }
+        __syncthreads();  // outputs complete, and nobody reads sk any more
+        const KeyT* const ro = so + tid + (tid >> 5);              // == merge_pad(tid + k * MERGE_THREADS) - k * 264
+        if (n_out == MERGE_TILE) {
+#pragma unroll
+            for (int k = 0; k < MERGE_ITEMS; ++k) dst[tid + k * MERGE_THREADS] = ro[k * (MERGE_THREADS + MERGE_THREADS / 32)] ^ sign;
+        } else {
+#pragma unroll
+            for (int k = 0; k < MERGE_ITEMS; ++k)
+                if (tid + k * MERGE_THREADS < n_out) dst[tid + k * MERGE_THREADS] = ro[k * (MERGE_THREADS + MERGE_THREADS / 32)] ^ sign;
+        }
+        if (!more) break;
+    }
+}
+
 }  // namespace rsb

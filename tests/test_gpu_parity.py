@@ -412,6 +412,31 @@ def test_merge_runs(rsb, gpu, oracle, t):
             assert np.array_equal(got, np.sort(np.concatenate((a, b)))), (t, len(a), len(b))
 
 
+@pytest.mark.parametrize("t", ["u32", "i64"])
+def test_merge_runs_many_tiles_per_cta(rsb, gpu, t):
+    # 8 jobs of very different sizes, ~3000 tiles: every persistent CTA walks several slots of the interleaved sequence
+    torch = _torch()
+    ctx, st = gpu
+    dt = numpy_dtype(t)
+    tdt = torch.int32 if dt.itemsize == 4 else torch.int64
+    rng = np.random.default_rng(11)
+    sizes = [(3_000_001, 2_500_000), (0, 900_000), (17, 4096 * 300), (1_234_567, 1), (4096 * 64, 4096 * 64), (5, 5), (700_000, 700_001), (0, 0)]
+    info = np.iinfo(dt)
+    runs = [(np.sort(rng.integers(info.min, info.max, size=na, dtype=dt, endpoint=True)),
+             np.sort(rng.integers(info.min // 2, info.max // 2, size=nb, dtype=dt))) for na, nb in sizes]
+    splits = torch.empty(1 << 14, dtype=torch.int64, device="cuda")
+    d_a = [_dev(a) if len(a) else torch.empty(1, dtype=tdt, device="cuda") for a, _ in runs]
+    d_b = [_dev(b) if len(b) else torch.empty(1, dtype=tdt, device="cuda") for _, b in runs]
+    d_o = [torch.empty(max(1, len(a) + len(b)), dtype=tdt, device="cuda") for a, b in runs]
+    torch.cuda.synchronize()
+    ctx.merge_runs(st, t, [(d_a[i].data_ptr(), len(runs[i][0]), d_b[i].data_ptr(), len(runs[i][1]), d_o[i].data_ptr())
+                           for i in range(len(runs))], splits.data_ptr(), splits.numel())
+    st.sync()
+    for i, (a, b) in enumerate(runs):
+        got = _host(d_o[i], dt)[:len(a) + len(b)]
+        assert np.array_equal(got, np.sort(np.concatenate((a, b)))), (t, i)
+
+
 # ---- BASELINE.json full sizes: size-independent properties, everything resident on the device -------
 
 def _full_size_case(rsb, gpu, t, kind, n, with_perm):
