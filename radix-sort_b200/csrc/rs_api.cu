@@ -614,7 +614,8 @@ static int merge_runs_typed(rs_context ctx, cudaStream_t st, bool is_signed, int
         unsigned long long max_tiles = 0;
         for (int j = 0; j < num_jobs; ++j) max_tiles = std::max(max_tiles, mb.tile_start[j + 1] - mb.tile_start[j]);
         if (max_tiles * num_jobs > 0xffffffffull) return fail(RS_CALCULATION_FAILED, "too many merge tiles");
-        const size_t smem = sizeof(KeyT) * (2 * MERGE_TILE + 4 * (MERGE_LINE_BYTES / sizeof(KeyT)) + MERGE_TILE / 32);
+        const size_t out_elems = sizeof(KeyT) == 4 ? MERGE_TILE + MERGE_TILE / 32 : MERGE_THREADS * (MERGE_ITEMS + 16 / sizeof(KeyT));
+        const size_t smem = sizeof(KeyT) * (MERGE_TILE + 4 * (MERGE_LINE_BYTES / sizeof(KeyT)) + out_elems);
         auto kern = rs_merge_tiles_pipelined_kernel<KeyT>;
         static thread_local int ctas_per_sm = 0;
         if (!ctas_per_sm) {

@@ -161,17 +161,18 @@ struct MergeSlot {          // per thread
 };
 
 template <typename KeyT>
-__global__ void __launch_bounds__(MERGE_THREADS, 4)
+__global__ void __launch_bounds__(MERGE_THREADS, sizeof(KeyT) == 4 ? 4 : 3)   // measured: 6 CTAs of 38 registers are slower than 4 of 64
 rs_merge_tiles_pipelined_kernel(const MergeBatch<KeyT> mb_param, const unsigned long long* __restrict__ splits,
                                 const uint32_t max_tiles_per_job) {
     constexpr uint32_t LINE = MERGE_LINE_BYTES / sizeof(KeyT);          // elements per line
     constexpr uint32_t VEC  = 16 / sizeof(KeyT);                        // elements per 16-byte load
     constexpr uint32_t SK   = MERGE_TILE + 4 * LINE;                    // staged inputs incl. alignment slack
+    constexpr uint32_t SO_STRIDE = MERGE_ITEMS + VEC;                   // outputs of one thread + one vector of padding
     constexpr int      ROWS = (MERGE_TILE + 3 * LINE + VEC * MERGE_THREADS - 1) / (VEC * MERGE_THREADS);
     extern __shared__ __align__(16) unsigned char merge_smem[];
     __shared__ MergeBatch<KeyT> mb;
     KeyT* const sk = reinterpret_cast<KeyT*>(merge_smem);   // [SK]                          virtual layout, see above
-    KeyT* const so = sk + SK;                               // [MERGE_TILE + MERGE_TILE/32]  transposed outputs
+    KeyT* const so = sk + SK;                               // [MERGE_THREADS * SO_STRIDE]   outputs (layout by key size, below)
     const int tid = threadIdx.x;
     if (tid == 0) mb = mb_param;
     __syncthreads();
@@ -274,22 +275,58 @@ rs_merge_tiles_pipelined_kernel(const MergeBatch<KeyT> mb_param, const unsigned 
         }
         uint32_t bi = diag - ai;
         KeyT     ka = sa[ai], kb = sb[bi];
-        KeyT* const wo = so + tid * MERGE_ITEMS + (tid >> 1);      // == merge_pad(tid * MERGE_ITEMS + k) - k
+        if constexpr (sizeof(KeyT) == 4) {
+            // 4-byte keys: scalar stores into the padded transpose as the merge goes (measured faster than vectors here)
+            KeyT* const wo = so + tid * MERGE_ITEMS + (tid >> 1);      // == merge_pad(tid * MERGE_ITEMS + k) - k
 #pragma unroll
-        for (int k = 0; k < MERGE_ITEMS; ++k) {
-            const bool take_a = (bi >= lb) || (ai < la && ka <= kb);
-            wo[k] = take_a ? ka : kb;
-            if (take_a) ka = sa[++ai]; else kb = sb[++bi];
-        }
-        __syncthreads();  // outputs complete, and nobody reads sk any more
-        const KeyT* const ro = so + tid + (tid >> 5);              // == merge_pad(tid + k * MERGE_THREADS) - k * 264
-        if (n_out == MERGE_TILE) {
+            for (int k = 0; k < MERGE_ITEMS; ++k) {
+                const bool take_a = (bi >= lb) || (ai < la && ka <= kb);
+                wo[k] = take_a ? ka : kb;
+                if (take_a) ka = sa[++ai]; else kb = sb[++bi];
+            }
+            __syncthreads();  // outputs complete, and nobody reads sk any more
+            const KeyT* const ro = so + tid + (tid >> 5);              // == merge_pad(tid + k * MERGE_THREADS) - k * 264
+            if (n_out == MERGE_TILE) {
 #pragma unroll
-            for (int k = 0; k < MERGE_ITEMS; ++k) dst[tid + k * MERGE_THREADS] = ro[k * (MERGE_THREADS + MERGE_THREADS / 32)] ^ sign;
+                for (int k = 0; k < MERGE_ITEMS; ++k) dst[tid + k * MERGE_THREADS] = ro[k * (MERGE_THREADS + MERGE_THREADS / 32)] ^ sign;
+            } else {
+#pragma unroll
+                for (int k = 0; k < MERGE_ITEMS; ++k)
+                    if (tid + k * MERGE_THREADS < n_out) dst[tid + k * MERGE_THREADS] = ro[k * (MERGE_THREADS + MERGE_THREADS / 32)] ^ sign;
+            }
         } else {
+            // 8-byte keys: thread t's MERGE_ITEMS outputs go to so[t * SO_STRIDE ...] with 16-byte stores; the one vector
+            // of padding per thread keeps these stores and the coalesced 16-byte reads below (almost) conflict-free
+            KeyT r[MERGE_ITEMS];
 #pragma unroll
-            for (int k = 0; k < MERGE_ITEMS; ++k)
-                if (tid + k * MERGE_THREADS < n_out) dst[tid + k * MERGE_THREADS] = ro[k * (MERGE_THREADS + MERGE_THREADS / 32)] ^ sign;
+            for (int k = 0; k < MERGE_ITEMS; ++k) {
+                const bool take_a = (bi >= lb) || (ai < la && ka <= kb);
+                r[k] = (take_a ? ka : kb) ^ sign;
+                if (take_a) ka = sa[++ai]; else kb = sb[++bi];
+            }
+            uint4* const wo = reinterpret_cast<uint4*>(so + tid * SO_STRIDE);
+#pragma unroll
+            for (int q = 0; q < MERGE_ITEMS / static_cast<int>(VEC); ++q) {
+                KeyT tmp[VEC];
+#pragma unroll
+                for (uint32_t e = 0; e < VEC; ++e) tmp[e] = r[q * VEC + e];
+                wo[q] = *reinterpret_cast<const uint4*>(tmp);
+            }
+            __syncthreads();  // outputs complete, and nobody reads sk any more
+            if (n_out == MERGE_TILE && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+                for (int k = 0; k < MERGE_TILE / static_cast<int>(VEC) / MERGE_THREADS; ++k) {
+                    const uint32_t i = (tid + k * MERGE_THREADS) * VEC;     // first output element of this vector
+                    reinterpret_cast<uint4*>(dst)[tid + k * MERGE_THREADS] =
+                        *reinterpret_cast<const uint4*>(so + (i / MERGE_ITEMS) * SO_STRIDE + (i % MERGE_ITEMS));
+                }
+            } else {   // ragged last tile of a job, or an output run that does not start on a 16-byte boundary
+#pragma unroll
+                for (int k = 0; k < MERGE_ITEMS; ++k) {
+                    const uint32_t i = tid + k * MERGE_THREADS;
+                    if (i < n_out) dst[i] = so[(i / MERGE_ITEMS) * SO_STRIDE + (i % MERGE_ITEMS)];
+                }
+            }
         }
         if (!more) break;
     }

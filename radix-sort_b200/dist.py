@@ -269,7 +269,8 @@ def _distributed_sort_p2p(keys, ops, dist, key_type: str, s, group):
         t = s.get(name)
         return t if (t is not None and t.numel() >= n) else ops.empty(max(n, 1))
 
-    gathered, other = buf("recv", n_recv), buf("c", n_recv)
+    slack = 32 * world   # the merge tree starts every intermediate run on a 128-byte line
+    gathered, other = buf("recv", n_recv + slack), buf("c", n_recv + slack)
     if n_recv == 0:
         out = gathered[:0]
     elif getattr(ops, "final_step", "merge") == "merge" and (world & (world - 1)) == 0:
@@ -309,6 +310,7 @@ def _merge_tree(ops, key_type, ptrs, counts, buf_x, buf_y, n_total, kb, scratch)
         jobs, nxt, off = [], [], 0
         for i in range(0, len(runs) - 1, 2):
             (pa, na), (pb, nb) = runs[i], runs[i + 1]
+            off = (off + 31) & ~31   # intermediate runs start on a 128-byte line: 16-byte stores now, aligned loads next level
             out_ptr = dst.data_ptr() + off * kb
             jobs.append((pa, na, pb, nb, out_ptr))
             nxt.append((out_ptr, na + nb))

@@ -437,6 +437,36 @@ def test_merge_runs_many_tiles_per_cta(rsb, gpu, t):
         assert np.array_equal(got, np.sort(np.concatenate((a, b)))), (t, i)
 
 
+@pytest.mark.parametrize("t,n_runs", [("u32", 8), ("i32", 4), ("u64", 8), ("u32", 2), ("i64", 1)])
+def test_merge_tree_levels(rsb, gpu, t, n_runs):
+    # the multi-GPU final step on ONE GPU: P sorted runs of uneven size (one empty) through dist._merge_tree
+    import importlib
+    import types
+    dsort = importlib.import_module("radix-sort_b200.dist")
+    torch = _torch()
+    ctx, st = gpu
+    dt = numpy_dtype(t)
+    kb = dt.itemsize
+    tdt = torch.int32 if kb == 4 else torch.int64
+    rng = np.random.default_rng(5)
+    info = np.iinfo(dt)
+    sizes = [300_001, 0, 123_457, 1, 70_000, 555_555, 4096, 250_003][:n_runs]
+    runs = [np.sort(rng.integers(info.min, info.max, size=n, dtype=dt, endpoint=True)) for n in sizes]
+    pool = _dev(np.concatenate(runs)) if sum(sizes) else torch.empty(1, dtype=tdt, device="cuda")
+    ptrs, off = [], 0
+    for n in sizes:   # runs sit back to back: arbitrary alignment, like the cut positions of a peer shard
+        ptrs.append(pool.data_ptr() + off * kb)
+        off += n
+    total = sum(sizes)
+    slack = 32 * n_runs
+    bx, by = (torch.empty(total + slack, dtype=tdt, device="cuda") for _ in range(2))
+    ops = types.SimpleNamespace(ctx=ctx, stream=st)
+    torch.cuda.synchronize()
+    out = dsort._merge_tree(ops, t, ptrs, sizes, bx, by, total, kb, {})
+    st.sync()
+    assert np.array_equal(_host(out, dt), np.sort(np.concatenate(runs)))
+
+
 # ---- BASELINE.json full sizes: size-independent properties, everything resident on the device -------
 
 def _full_size_case(rsb, gpu, t, kind, n, with_perm):
