@@ -607,8 +607,37 @@ static int merge_runs_typed(rs_context ctx, cudaStream_t st, bool is_signed, int
     if (tiles > 0x7fffffffull) return fail(RS_CALCULATION_FAILED, "too many merge tiles");
     const unsigned long long boundaries = tiles + num_jobs;
     const int pgrid = static_cast<int>(std::min<unsigned long long>((boundaries + 255) / 256, static_cast<unsigned long long>(ctx->sm_count) * 32));
-    rs_merge_partition_kernel<KeyT><<<pgrid, 256, 0, st>>>(mb, reinterpret_cast<unsigned long long*>(d_splits));
+    // developer switch (like RSB200_DIST_TIMING in dist.py): device time of the two kernels, printed to stderr; adds syncs
+    static const bool merge_timing = std::getenv("RSB200_MERGE_TIMING") != nullptr;
+    cudaEvent_t tev[3] = {nullptr, nullptr, nullptr};
+    if (merge_timing) {
+        for (auto& e : tev) cudaEventCreate(&e);
+        cudaEventRecord(tev[0], st);
+    }
+    static const bool flat_partition = std::getenv("RSB200_MERGE_FLAT_PARTITION") != nullptr;  // A/B switch for profiling
+    if (flat_partition || tiles <= 4 * MERGE_COARSE) {
+        rs_merge_partition_kernel<KeyT><<<pgrid, 256, 0, st>>>(mb, reinterpret_cast<unsigned long long*>(d_splits), 0);
+    } else {
+        rs_merge_partition_kernel<KeyT><<<pgrid, 256, 0, st>>>(mb, reinterpret_cast<unsigned long long*>(d_splits), 1);
+        rs_merge_partition_kernel<KeyT><<<pgrid, 256, 0, st>>>(mb, reinterpret_cast<unsigned long long*>(d_splits), 2);
+    }
     RS_CUDA(cudaGetLastError(), RS_CALCULATION_FAILED);
+    if (merge_timing) cudaEventRecord(tev[1], st);
+    struct TimingReport {
+        cudaEvent_t* ev; cudaStream_t st; bool on; unsigned long long tiles;
+        ~TimingReport() {
+            if (!on) return;
+            cudaEventRecord(ev[2], st);
+            cudaEventSynchronize(ev[2]);
+            float part = 0.f, tile = 0.f;
+            cudaEventElapsedTime(&part, ev[0], ev[1]);
+            cudaEventElapsedTime(&tile, ev[1], ev[2]);
+            int dev = 0;
+            cudaGetDevice(&dev);
+            std::fprintf(stderr, "[rsb200 merge, device %d] %llu tiles: partition %.3f ms, tiles %.3f ms\n", dev, tiles, part, tile);
+            for (int i = 0; i < 3; ++i) cudaEventDestroy(ev[i]);
+        }
+    } timing_report{tev, st, merge_timing, tiles};
     static const bool one_tile_per_cta = std::getenv("RSB200_MERGE_UNPIPELINED") != nullptr;  // A/B switch for profiling
     if (!one_tile_per_cta) {
         unsigned long long max_tiles = 0;
@@ -616,8 +645,21 @@ static int merge_runs_typed(rs_context ctx, cudaStream_t st, bool is_signed, int
         if (max_tiles * num_jobs > 0xffffffffull) return fail(RS_CALCULATION_FAILED, "too many merge tiles");
         const size_t out_elems = sizeof(KeyT) == 4 ? MERGE_TILE + MERGE_TILE / 32 : MERGE_THREADS * (MERGE_ITEMS + 16 / sizeof(KeyT));
         const size_t smem = sizeof(KeyT) * (MERGE_TILE + 4 * (MERGE_LINE_BYTES / sizeof(KeyT)) + out_elems);
-        auto kern = rs_merge_tiles_pipelined_kernel<KeyT>;
-        static thread_local int ctas_per_sm = 0;
+        // runs in peer memory (multi-GPU level 1) want the variant with more CTAs, i.e. more loads in flight
+        bool remote = false;
+        int  here = 0;
+        cudaGetDevice(&here);
+        for (int j = 0; j < num_jobs && !remote; ++j)
+            for (const void* p : {a_ptrs[j], b_ptrs[j]}) {
+                cudaPointerAttributes at{};
+                if (p && cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device != here) remote = true;
+            }
+        cudaGetLastError();  // a pointer the runtime does not know is simply treated as local
+        static const char* const force = std::getenv("RSB200_MERGE_DENSE");  // "0" / "1": A/B switch for profiling
+        if (force) remote = force[0] == '1';
+        auto kern = remote ? rs_merge_tiles_pipelined_kernel<KeyT, true> : rs_merge_tiles_pipelined_kernel<KeyT, false>;
+        static thread_local int occupancy[2] = {0, 0};
+        int& ctas_per_sm = occupancy[remote ? 1 : 0];
         if (!ctas_per_sm) {
             RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)), RS_CALCULATION_FAILED);
             RS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, MERGE_THREADS, smem), RS_CALCULATION_FAILED);

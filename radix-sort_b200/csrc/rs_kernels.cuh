@@ -259,19 +259,23 @@ rs_gather_histogram_kernel(const SegmentTable<KeyT> seg, KeyT* __restrict__ gath
 #pragma unroll
         for (int j = 0; j < MAX_SEGMENTS; ++j)
             if (j == sidx) { src = seg.ptr[j]; beg = seg.start[j]; end = seg.start[j + 1]; }
-        const unsigned long long cnt = end - beg;
-        KeyT* const              dst = gathered + beg;
+        // A warp load that straddles 128-byte lines runs at about half speed over NVLink (tools/peerbw.cu): index
+        // the segment from the start of its first line (`skew` elements early) so that lane 0 sits on a line boundary.
+        const unsigned long long skew = (reinterpret_cast<uintptr_t>(src) / sizeof(KeyT)) & (128 / sizeof(KeyT) - 1);
+        const unsigned long long cnt  = end - beg + skew;
+        const KeyT* const        from = src - skew;
+        KeyT* const              dst  = gathered + beg - skew;
         for (unsigned long long base = first; base < cnt; base += stride * GATHER_UNROLL) {
             KeyT v[GATHER_UNROLL];
 #pragma unroll
             for (int u = 0; u < GATHER_UNROLL; ++u) {
                 const unsigned long long i = base + u * stride;
-                if (i < cnt) v[u] = src[i];  // NVLink (or local) read
+                if (i >= skew && i < cnt) v[u] = from[i];  // NVLink (or local) read
             }
 #pragma unroll
             for (int u = 0; u < GATHER_UNROLL; ++u) {
                 const unsigned long long i = base + u * stride;
-                if (i < cnt) {
+                if (i >= skew && i < cnt) {
                     dst[i] = v[u];
 #pragma unroll
                     for (int p = 0; p < NPASS; ++p)

@@ -47,11 +47,15 @@ __device__ __forceinline__ void merge_job_of(const MergeBatch<KeyT>& mb, unsigne
         if (j == job) { a = mb.a[j]; b = mb.b[j]; out = mb.out[j]; na = mb.na[j]; nb = mb.nb[j]; first_tile = mb.tile_start[j]; }
 }
 
-// number of elements taken from A among the first `diag` outputs of merge(A, B); ties take A first
+// number of elements taken from A among the first `diag` outputs of merge(A, B); ties take A first.
+// [lo_hint, hi_hint] brackets the answer (0 .. na when nothing is known).
 template <typename KeyT, typename IndexT>
-__device__ __forceinline__ IndexT merge_path(const KeyT* a, IndexT na, const KeyT* b, IndexT nb, IndexT diag, KeyT sign) {
+__device__ __forceinline__ IndexT merge_path(const KeyT* a, IndexT na, const KeyT* b, IndexT nb, IndexT diag, KeyT sign,
+                                             IndexT lo_hint, IndexT hi_hint) {
     IndexT lo = diag > nb ? diag - nb : 0;
     IndexT hi = diag < na ? diag : na;
+    if (lo < lo_hint) lo = lo_hint;
+    if (hi > hi_hint) hi = hi_hint;
     while (lo < hi) {
         const IndexT mid = lo + ((hi - lo) >> 1);
         const KeyT   ka  = a[mid] ^ sign;
@@ -60,10 +64,20 @@ __device__ __forceinline__ IndexT merge_path(const KeyT* a, IndexT na, const Key
     }
     return lo;
 }
+template <typename KeyT, typename IndexT>
+__device__ __forceinline__ IndexT merge_path(const KeyT* a, IndexT na, const KeyT* b, IndexT nb, IndexT diag, KeyT sign) {
+    return merge_path<KeyT, IndexT>(a, na, b, nb, diag, sign, 0, na);
+}
 
-// splits[job_first_boundary + i] = A-count of the first i*MERGE_TILE outputs of the job, i = 0 .. tiles_of_job
+// splits[job_first_boundary + i] = A-count of the first i*MERGE_TILE outputs of the job, i = 0 .. tiles_of_job.
+// Every probe of a run in peer memory is a 32-byte NVLink read, so the search runs in two launches: `phase` 1 finds
+// every MERGE_COARSE-th boundary (and the last one of each job) over the whole runs, `phase` 2 the others between
+// their two coarse neighbours (the path is monotone) -- 18 instead of up to 32 steps for 2^31-key runs.  `phase` 0
+// = everything in one launch over the whole runs.
+constexpr unsigned long long MERGE_COARSE = 64;
+
 template <typename KeyT>
-__global__ void rs_merge_partition_kernel(const MergeBatch<KeyT> mb, unsigned long long* __restrict__ splits) {
+__global__ void rs_merge_partition_kernel(const MergeBatch<KeyT> mb, unsigned long long* __restrict__ splits, const int phase) {
     const unsigned long long total_boundaries = mb.tile_start[mb.num_jobs] + mb.num_jobs;
     for (unsigned long long g = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; g < total_boundaries;
          g += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
@@ -72,13 +86,23 @@ __global__ void rs_merge_partition_kernel(const MergeBatch<KeyT> mb, unsigned lo
 #pragma unroll
         for (int j = 1; j < MERGE_MAX_JOBS; ++j)
             if (j < mb.num_jobs && g >= mb.tile_start[j] + j) job = j;
-        const KeyT* a = nullptr; const KeyT* b = nullptr; unsigned long long na = 0, nb = 0, first = 0;
+        const KeyT* a = nullptr; const KeyT* b = nullptr; unsigned long long na = 0, nb = 0, first = 0, tiles = 0;
 #pragma unroll
         for (int j = 0; j < MERGE_MAX_JOBS; ++j)
-            if (j == job) { a = mb.a[j]; b = mb.b[j]; na = mb.na[j]; nb = mb.nb[j]; first = mb.tile_start[j] + j; }
-        unsigned long long diag = (g - first) * MERGE_TILE;
+            if (j == job) { a = mb.a[j]; b = mb.b[j]; na = mb.na[j]; nb = mb.nb[j]; first = mb.tile_start[j] + j; tiles = mb.tile_start[j + 1] - mb.tile_start[j]; }
+        const unsigned long long i = g - first;                       // boundary index within the job, 0 .. tiles
+        const bool coarse = (i % MERGE_COARSE) == 0 || i == tiles;
+        if (phase != 0 && coarse != (phase == 1)) continue;
+        unsigned long long diag = i * MERGE_TILE;
         if (diag > na + nb) diag = na + nb;
-        splits[g] = merge_path<KeyT, unsigned long long>(a, na, b, nb, diag, mb.sign);
+        unsigned long long lo_hint = 0, hi_hint = na;
+        if (phase == 2) {
+            const unsigned long long prev = i - i % MERGE_COARSE;
+            const unsigned long long next = prev + MERGE_COARSE < tiles ? prev + MERGE_COARSE : tiles;
+            lo_hint = splits[first + prev];
+            hi_hint = splits[first + next];
+        }
+        splits[g] = merge_path<KeyT, unsigned long long>(a, na, b, nb, diag, mb.sign, lo_hint, hi_hint);
     }
 }
 
@@ -160,8 +184,11 @@ struct MergeSlot {          // per thread
     uint32_t           total;  // span_a + span_b
 };
 
-template <typename KeyT>
-__global__ void __launch_bounds__(MERGE_THREADS, sizeof(KeyT) == 4 ? 4 : 3)   // measured: 6 CTAs of 38 registers are slower than 4 of 64
+// DENSE = more resident CTAs with fewer registers each (4-byte keys: 6 x 38 registers instead of 4 x 64).  Slower
+// when both runs are local (2.56 vs 2.26 ms per 2^30 keys) but it holds 1.5x the bytes in flight, which is what bounds
+// a level whose runs live in peer memory; the host picks it when an input pointer belongs to another device.
+template <typename KeyT, bool DENSE>
+__global__ void __launch_bounds__(MERGE_THREADS, sizeof(KeyT) == 4 ? (DENSE ? 6 : 4) : 3)
 rs_merge_tiles_pipelined_kernel(const MergeBatch<KeyT> mb_param, const unsigned long long* __restrict__ splits,
                                 const uint32_t max_tiles_per_job) {
     constexpr uint32_t LINE = MERGE_LINE_BYTES / sizeof(KeyT);          // elements per line
