@@ -200,7 +200,11 @@ int rs_sorter_sort_segments_device(rs_sorter s, rs_stream st, int num_segments, 
 /* One level of pairwise merges of sorted key runs (the multi-GPU final step, SURVEY.md 8e.5: "or a P-way merge"):
  * job j merges a[j] (a_counts[j] keys) and b[j] into out[j]; inputs may be peer memory (rs_ipc_open), so the first
  * level is exchange and merge in one kernel.  d_splits: device scratch of splits_capacity uint64
- * (>= sum over jobs of ceil((na+nb)/4096) + num_jobs).  Keys only; order is the key type's. */
+ * (>= sum over jobs of ceil((na+nb)/4096) + num_jobs).  Keys only; order is the key type's.
+ * Runs may start at any element.  The kernel reads WHOLE 128-byte lines (every line that holds at least one key of
+ * a run, nothing else), so a run must not end in the last partial line of a mapping -- cudaMalloc, rs_device_alloc
+ * and torch's allocator all hand out multiples of 256 bytes or more.  Outputs that start on a 16-byte boundary take
+ * the vector store path (8-byte keys). */
 int rs_merge_runs_device(rs_context ctx, rs_stream st, rs_key_type type, int num_jobs, const void* const* d_a_ptrs,
                          const uint64_t* a_counts, const void* const* d_b_ptrs, const uint64_t* b_counts,
                          void* const* d_out_ptrs, uint64_t* d_splits, uint64_t splits_capacity);
