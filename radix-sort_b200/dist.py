@@ -115,12 +115,14 @@ class RawBuf:
         return self._n
 
 
-def plan_exchange(sorted_keys, ops, dist, key_type: str, group=None, device=None):
+def plan_exchange(sorted_keys, ops, dist, key_type: str, group=None, device=None, need_recv_counts: bool = True):
     """Exact splitters + per-destination cut positions in this rank's sorted shard.
 
     Returns (cuts, recv_counts): cuts has world+1 entries (cuts[0]=0, cuts[-1]=n_local); rank d receives
     sorted_keys[cuts[d]:cuts[d+1]] from this rank.  Rank j ends with the keys whose global (stable) rank
     lies in [j*N/P, (j+1)*N/P), so shard sizes differ by at most one key whatever the distribution.
+    recv_counts is None when need_recv_counts is False (the peer-memory path learns them from the cut table it
+    gathers anyway, which saves one collective and one host sync).
     """
     import torch
     world = dist.get_world_size(group)
@@ -143,10 +145,9 @@ def plan_exchange(sorted_keys, ops, dist, key_type: str, group=None, device=None
             pos[is_top] = n_local
         return pos
 
-    n_total = int(allreduce_np(np.array([n_local]))[0])
     if world == 1:
         return np.array([0, n_local], dtype=np.int64), np.array([n_local], dtype=np.int64)
-    targets = [(j * n_total) // world for j in range(1, world)]  # global rank of the first key of rank j
+    targets = None               # global rank of the first key of rank j; known after the first all-reduce
     prefix = [0] * (world - 1)   # per splitter: ordered-unsigned key bits resolved so far
     below = [0] * (world - 1)    # per splitter: number of keys globally below `prefix`
     resolved = 0                 # key bits (from the top) already fixed in every splitter prefix
@@ -162,6 +163,9 @@ def plan_exchange(sorted_keys, ops, dist, key_type: str, group=None, device=None
         is_top[:, -1] = [b + (fan << shift) >= top for b in bases]         # the last boundary may be `top` itself
         pos = positions(q.reshape(-1), is_top.reshape(-1)).reshape(q.shape)
         counts = allreduce_np(np.diff(pos, axis=1))   # [len(bases)][fan] global sub-range counts
+        if level == 0:   # the level-0 histogram covers the whole key space, so it also tells N (no extra all-reduce)
+            n_total = int(counts[0].sum())
+            targets = [(j * n_total) // world for j in range(1, world)]
         for j in range(world - 1):
             c = counts[0 if level == 0 else j]
             cum = below[j] + np.concatenate(([0], np.cumsum(c)))
@@ -180,7 +184,7 @@ def plan_exchange(sorted_keys, ops, dist, key_type: str, group=None, device=None
     mine = torch.from_numpy(np.ascontiguousarray(eq_local, dtype=np.int64)).to(dev)
     parts = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(parts, mine, group=group)
-    eq_all = np.stack([p.cpu().numpy() for p in parts])  # [rank][splitter]
+    eq_all = torch.stack(parts).cpu().numpy()  # [rank][splitter], one device->host copy
     cuts = np.zeros(world + 1, dtype=np.int64)
     cuts[-1] = n_local
     for j in range(world - 1):
@@ -189,6 +193,8 @@ def plan_exchange(sorted_keys, ops, dist, key_type: str, group=None, device=None
         share = min(max(need_left - before_me, 0), int(eq_local[j]))
         cuts[j + 1] = lb[j] + share
     cuts = np.maximum.accumulate(cuts)  # equal splitters (heavy duplicates) keep the cuts monotone
+    if not need_recv_counts:
+        return cuts, None
     t_send = torch.from_numpy(np.diff(cuts).copy()).to(dev)
     t_recv = torch.empty_like(t_send)
     dist.all_to_all_single(t_recv, t_send, group=group)
@@ -251,13 +257,13 @@ def _distributed_sort_p2p(keys, ops, dist, key_type: str, s, group):
     sorted_local = RawBuf(ops.p2p_local[sel], n_local, device=keys.device)
     mark("local sort")
     # 2. exact splitters (all-reduces inside: every peer's local sort is complete once they return)
-    cuts, _ = plan_exchange(sorted_local, ops, dist, key_type, group=group, device=keys.device)
+    cuts, _ = plan_exchange(sorted_local, ops, dist, key_type, group=group, device=keys.device, need_recv_counts=False)
     mark("splitters")
     # 3. everybody learns everybody's cut positions and buffer selector
     mine = torch.from_numpy(np.concatenate((cuts, [sel])).astype(np.int64)).to(keys.device)
     parts = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(parts, mine, group=group)
-    table = np.stack([p.cpu().numpy() for p in parts])  # [source][world+1 cuts, sel]
+    table = torch.stack(parts).cpu().numpy()  # [source][world+1 cuts, sel], one device->host copy
     ptrs, counts = [], []
     for src in range(world):
         lo, hi = int(table[src, rank]), int(table[src, rank + 1])
