@@ -4,7 +4,8 @@ The product is the C-ABI shared library ``librsb200.so`` (``include/rsb200.h``, 
 ``csrc/``) and the C++ facade in ``cpp/`` that keeps the reference's class names
 (``RadixSortGPU<T>``, ``ComputeDeviceData<T>``, ``CRadixSortTask<T>``, ``IComputeTask`` ...).
 This Python package is the thin ctypes binding the tests and ``bench.py`` drive the library
-through, plus the multi-GPU host logic (one process per GPU over ``torch.distributed``).
+through, plus the multi-GPU host logic (``dist``: one process per GPU over ``torch.distributed``) and the torch
+entry ``torch_op.sort(tensor) -> (values, indices)``.
 
 The directory name contains a hyphen, so import it with
 ``importlib.import_module("radix-sort_b200")`` (see ``tests/conftest.py``).

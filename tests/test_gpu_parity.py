@@ -536,3 +536,32 @@ def test_more_than_one_lookback_chunk(rsb, gpu):
     # > 2^30 keys: the look-back chain restarts at a chunk boundary with offsets from the chunk histograms
     _full_size_case(rsb, gpu, "u32", "uniform", (1 << 30) + 77777, with_perm=False)
     _full_size_case(rsb, gpu, "u32", "zeros", (1 << 30) + 8192 * 3 + 1, with_perm=False)
+
+
+@pytest.mark.parametrize("dt_name", ["int32", "int64", "uint32", "uint64"])
+def test_torch_sort_operator(rsb, dt_name):
+    # sort(tensor) -> (values, indices), zero copy on torch's current stream (radix-sort_b200/torch_op.py)
+    import importlib
+    op = importlib.import_module("radix-sort_b200.torch_op")
+    torch = _torch()
+    dt = getattr(torch, dt_name)
+    np_dt = np.dtype(dt_name)
+    rng = np.random.default_rng(21)
+    info = np.iinfo(np_dt)
+    for n, lo, hi in ((1, info.min, info.max), (5000, info.min, info.max), (300_000, 0, 50), (1 << 21, info.min, info.max)):
+        host = rng.integers(lo, hi, size=n, dtype=np_dt, endpoint=True)
+        keys = torch.from_numpy(host.view(np.int32 if np_dt.itemsize == 4 else np.int64).copy()).cuda().view(dt)
+        values, indices = op.sort(keys)
+        torch.cuda.synchronize()
+        order = np.argsort(host, kind="stable")
+        assert values.dtype == dt and indices.dtype == torch.int32
+        got_v = values.view(torch.int32 if np_dt.itemsize == 4 else torch.int64).cpu().numpy().view(np_dt)
+        assert np.array_equal(got_v, host[order]), (dt_name, n)
+        assert np.array_equal(indices.cpu().numpy().astype(np.int64), order), (dt_name, n)
+        keys_only, none = op.sort(keys, return_indices=False)
+        torch.cuda.synchronize()
+        assert none is None
+        assert np.array_equal(keys_only.view(torch.int32 if np_dt.itemsize == 4 else torch.int64).cpu().numpy().view(np_dt), host[order])
+        assert np.array_equal(keys.view(torch.int32 if np_dt.itemsize == 4 else torch.int64).cpu().numpy().view(np_dt), host)  # input untouched
+    with pytest.raises(ValueError):
+        op.sort(torch.arange(4, dtype=torch.int32))   # CPU tensor: no fallback

@@ -1,0 +1,97 @@
+"""Host logic of the torch entry (radix-sort_b200/torch_op.py) with a numpy test double as the backend: argument
+checks, sorter cache growth, which ping-pong buffer is returned.  The product backend (librsb200.so) is exercised by
+tests/test_gpu_parity.py::test_torch_sort_operator on the GPU."""
+import ctypes
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+
+class _FakeStream:
+    def sync(self):
+        pass
+
+
+class _FakeSorter:
+    """Stands in for capi.Sorter: stable sort with numpy on the raw host pointers it is given; result in buffer 1."""
+    created = []
+
+    def __init__(self, key_type, capacity):
+        self.np_dt = {"u32": np.uint32, "i32": np.int32, "u64": np.uint64, "i64": np.int64}[key_type]
+        self.capacity, self.closed = capacity, False
+        _FakeSorter.created.append(self)
+
+    def _view(self, ptr, n, dt):
+        return np.ctypeslib.as_array((ctypes.c_uint8 * (n * np.dtype(dt).itemsize)).from_address(ptr)).view(dt)
+
+    def sort_device(self, stream, d_in, d_buf0, d_buf1, n, d_vin=None, d_vbuf0=None, d_vbuf1=None):
+        assert not self.closed and n <= self.capacity
+        keys = self._view(d_in, n, self.np_dt)
+        order = np.argsort(keys, kind="stable")
+        self._view(d_buf1, n, self.np_dt)[:] = keys[order]
+        self._view(d_buf0, n, self.np_dt)[:] = 0
+        if d_vin is not None:
+            self._view(d_vbuf1, n, np.int32)[:] = self._view(d_vin, n, np.int32)[order]
+        return 1
+
+    def close(self):
+        self.closed = True
+
+
+class _FakeBackend:
+    def stream(self, cuda_stream):
+        return _FakeStream()
+
+    def make_sorter(self, key_type, capacity):
+        return _FakeSorter(key_type, capacity)
+
+
+@pytest.fixture()
+def op():
+    return importlib.import_module("radix-sort_b200.torch_op")
+
+
+def test_sort_values_and_stable_indices(op):
+    ts = op.TorchSorter(0, backend=_FakeBackend())
+    rng = np.random.default_rng(0)
+    for dt in (torch.int32, torch.int64):
+        keys = torch.from_numpy(rng.integers(-5, 5, size=1000)).to(dt)
+        before = keys.clone()
+        values, indices = ts.sort(keys)
+        ref_v, ref_i = torch.sort(keys, stable=True)
+        assert torch.equal(values, ref_v) and torch.equal(indices.long(), ref_i) and indices.dtype == torch.int32
+        assert torch.equal(keys, before)
+        values2, none = ts.sort(keys, return_indices=False)
+        assert none is None and torch.equal(values2, ref_v)
+    ts.close()
+
+
+def test_sorter_cache_grows_and_is_reused(op):
+    _FakeSorter.created.clear()
+    ts = op.TorchSorter(0, backend=_FakeBackend())
+    ts.sort(torch.arange(10, dtype=torch.int32))
+    ts.sort(torch.arange(100, dtype=torch.int32))
+    assert len(_FakeSorter.created) == 1 and _FakeSorter.created[0].capacity >= 1 << 20
+    big = (1 << 20) + 5
+    ts.sort(torch.zeros(big, dtype=torch.int32), return_indices=False)
+    assert len(_FakeSorter.created) == 2 and _FakeSorter.created[0].closed and _FakeSorter.created[1].capacity >= big
+    ts.sort(torch.arange(7, dtype=torch.int64))
+    assert len(_FakeSorter.created) == 3   # another key type, another sorter
+    ts.close()
+    assert all(s.closed for s in _FakeSorter.created)
+
+
+def test_argument_checks(op):
+    ts = op.TorchSorter(0, backend=_FakeBackend())
+    with pytest.raises(TypeError):
+        ts.sort(torch.zeros(4, dtype=torch.float32))
+    with pytest.raises(ValueError):
+        ts.sort(torch.zeros((2, 2), dtype=torch.int32))
+    with pytest.raises(ValueError):
+        ts.sort(torch.arange(10, dtype=torch.int32)[::2])
+    v, i = ts.sort(torch.empty(0, dtype=torch.int64))
+    assert v.numel() == 0 and i.numel() == 0
+    with pytest.raises(ValueError):       # the module-level entry is the product path: CUDA tensors only, no CPU fallback
+        op.sort(torch.arange(4, dtype=torch.int32))
