@@ -25,6 +25,14 @@ using namespace rsb;
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_last_error;
 
+// cudaFuncSetAttribute is a per-device setting: launch helpers remember, per call site and thread, on which devices
+// their kernel has been configured (a process may hold contexts on several GPUs).
+static uint64_t current_device_bit() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return 1ull << (dev & 63);
+}
+
 static int fail(int status, const char* what, cudaError_t e = cudaSuccess) {
     char buf[512];
     if (e != cudaSuccess)
@@ -194,12 +202,12 @@ template <typename KeyT, int NPASS>
 static cudaError_t launch_hist_n(int grid, cudaStream_t st, const KeyT* keys, uint64_t n, const Plan&,
                                  unsigned long long* hist, const PassTable& pt) {
     auto kern = rs_histogram_kernel<KeyT, NPASS>;
-    static thread_local bool configured = false;
-    if (!configured) {
+    static thread_local uint64_t configured = 0;
+    if (const uint64_t bit = current_device_bit(); !(configured & bit)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(HistCfg<NPASS>::bytes));
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured |= bit;
     }
     kern<<<grid, HIST_THREADS, HistCfg<NPASS>::bytes, st>>>(keys, n, hist, pt);
     return cudaGetLastError();
@@ -230,12 +238,12 @@ template <typename KeyT, int NPASS>
 static cudaError_t launch_gather_hist_n(int grid, cudaStream_t st, const SegmentTable<KeyT>& seg, KeyT* gathered,
                                         unsigned long long* hist, const PassTable& pt) {
     auto kern = rs_gather_histogram_kernel<KeyT, NPASS>;
-    static thread_local bool configured = false;
-    if (!configured) {
+    static thread_local uint64_t configured = 0;
+    if (const uint64_t bit = current_device_bit(); !(configured & bit)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(HistCfg<NPASS>::bytes));
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured |= bit;
     }
     kern<<<grid, HIST_THREADS, HistCfg<NPASS>::bytes, st>>>(seg, gathered, hist, pt);
     return cudaGetLastError();
@@ -325,14 +333,14 @@ static int sort_typed(rs_sorter s, cudaStream_t st, const KeyT* in, KeyT* buf0, 
         cudaError_t e;
         if (has_vals) {
             auto kern = rs_small_sort_kernel<KeyT, true>;
-            static thread_local bool cfg = false;
-            if (!cfg) { RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SmallSmem<KeyT, true>::total)), RS_CALCULATION_FAILED); cfg = true; }
+            static thread_local uint64_t cfg = 0;
+            if (const uint64_t bit = current_device_bit(); !(cfg & bit)) { RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SmallSmem<KeyT, true>::total)), RS_CALCULATION_FAILED); cfg |= bit; }
             kern<<<1, SMALL_THREADS, SmallSmem<KeyT, true>::total, st>>>(in, kout, vin, vout, static_cast<uint32_t>(n), pt, hist_s, plan_s, allow);
             e = cudaGetLastError();
         } else {
             auto kern = rs_small_sort_kernel<KeyT, false>;
-            static thread_local bool cfg = false;
-            if (!cfg) { RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SmallSmem<KeyT, false>::total)), RS_CALCULATION_FAILED); cfg = true; }
+            static thread_local uint64_t cfg = 0;
+            if (const uint64_t bit = current_device_bit(); !(cfg & bit)) { RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SmallSmem<KeyT, false>::total)), RS_CALCULATION_FAILED); cfg |= bit; }
             kern<<<1, SMALL_THREADS, SmallSmem<KeyT, false>::total, st>>>(in, kout, nullptr, nullptr, static_cast<uint32_t>(n), pt, hist_s, plan_s, allow);
             e = cudaGetLastError();
         }
@@ -658,8 +666,8 @@ static int merge_runs_typed(rs_context ctx, cudaStream_t st, bool is_signed, int
         static const char* const force = std::getenv("RSB200_MERGE_DENSE");  // "0" / "1": A/B switch for profiling
         if (force) remote = force[0] == '1';
         auto kern = remote ? rs_merge_tiles_pipelined_kernel<KeyT, true> : rs_merge_tiles_pipelined_kernel<KeyT, false>;
-        static thread_local int occupancy[2] = {0, 0};
-        int& ctas_per_sm = occupancy[remote ? 1 : 0];
+        static thread_local int occupancy[2][64] = {};   // per variant and device
+        int& ctas_per_sm = occupancy[remote ? 1 : 0][here & 63];
         if (!ctas_per_sm) {
             RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)), RS_CALCULATION_FAILED);
             RS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, MERGE_THREADS, smem), RS_CALCULATION_FAILED);
@@ -672,10 +680,10 @@ static int merge_runs_typed(rs_context ctx, cudaStream_t st, bool is_signed, int
     }
     const size_t smem = sizeof(KeyT) * (MERGE_TILE + MERGE_TILE / 32);
     auto kern = rs_merge_tiles_kernel<KeyT>;
-    static thread_local bool configured = false;
-    if (!configured) {
+    static thread_local uint64_t configured = 0;
+    if (const uint64_t bit = current_device_bit(); !(configured & bit)) {
         RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)), RS_CALCULATION_FAILED);
-        configured = true;
+        configured |= bit;
     }
     kern<<<static_cast<unsigned>(tiles), MERGE_THREADS, smem, st>>>(mb, reinterpret_cast<const unsigned long long*>(d_splits));
     RS_CUDA(cudaGetLastError(), RS_CALCULATION_FAILED);
