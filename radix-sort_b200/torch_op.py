@@ -6,6 +6,11 @@ tensors are the sorter's ping-pong buffers themselves (no copy); ``indices`` is 
 (``torch.sort(stable=True)`` semantics), stored as int32 bit patterns of the library's uint32 payload, so inputs
 are limited to 2^31 - 1 keys when indices are requested.
 
+float32 / float64 keys (additive: the reference excludes floats, doc/doc.tex:64) are sorted through the
+usual order-preserving bit transform -- flip the magnitude bits of negative values, then sort as signed integers --
+applied with two elementwise torch ops around the integer sort; the C ABI itself stays integer-only.  Order is the
+IEEE total order of the bit patterns: -NaN < -inf < ... < -0.0 < +0.0 < ... < +inf < +NaN.
+
 There is no CPU fallback: a tensor that is not on a CUDA device, or a missing ``librsb200.so``, raises.
 The reference has no counterpart (its user entry is examples/basic_sort/basic_sort.cpp:24-139, host buffers only).
 """
@@ -16,6 +21,12 @@ import threading
 from . import capi
 
 _KEY_OF_DTYPE = {"torch.int32": "i32", "torch.int64": "i64", "torch.uint32": "u32", "torch.uint64": "u64"}
+_INT_OF_FLOAT = {"torch.float32": ("int32", 31), "torch.float64": ("int64", 63)}
+
+
+def _float_to_ordered(bits, sign_shift: int):
+    """Signed-integer view of IEEE bits -> signed integers in the same order (its own inverse)."""
+    return bits ^ ((bits >> sign_shift) & ((1 << sign_shift) - 1))   # arithmetic shift: all-ones mask for negatives
 
 
 class _NativeBackend:
@@ -56,9 +67,16 @@ class TorchSorter:
 
     def sort(self, keys, return_indices: bool = True):
         import torch
+        as_float = _INT_OF_FLOAT.get(str(keys.dtype))
+        if as_float is not None:
+            if keys.dim() != 1 or not keys.is_contiguous():
+                raise ValueError("keys must be a contiguous 1-D tensor")
+            int_dtype, sign_shift = getattr(torch, as_float[0]), as_float[1]
+            ordered, indices = self.sort(_float_to_ordered(keys.view(int_dtype), sign_shift), return_indices)
+            return _float_to_ordered(ordered, sign_shift).view(keys.dtype), indices
         key_type = _KEY_OF_DTYPE.get(str(keys.dtype))
         if key_type is None:
-            raise TypeError(f"unsupported key dtype {keys.dtype}: int32, int64, uint32, uint64")
+            raise TypeError(f"unsupported key dtype {keys.dtype}: int32, int64, uint32, uint64, float32, float64")
         if keys.dim() != 1 or not keys.is_contiguous():
             raise ValueError("keys must be a contiguous 1-D tensor")
         if self.backend.__class__ is _NativeBackend and not keys.is_cuda:
@@ -94,7 +112,7 @@ _per_device: dict[int, TorchSorter] = {}
 
 
 def sort(keys, return_indices: bool = True):
-    """Ascending sort of a 1-D CUDA tensor of int32/int64/uint32/uint64 keys.
+    """Ascending sort of a 1-D CUDA tensor of int32/int64/uint32/uint64 (or float32/float64, see the module text) keys.
 
     Returns ``(values, indices)``; ``indices`` (int32) is the stable permutation with ``keys[indices] == values``,
     or ``None`` when ``return_indices`` is False (keys-only sorts run ~1.7x faster).  The work is enqueued on

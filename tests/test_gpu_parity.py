@@ -565,3 +565,18 @@ def test_torch_sort_operator(rsb, dt_name):
         assert np.array_equal(keys.view(torch.int32 if np_dt.itemsize == 4 else torch.int64).cpu().numpy().view(np_dt), host)  # input untouched
     with pytest.raises(ValueError):
         op.sort(torch.arange(4, dtype=torch.int32))   # CPU tensor: no fallback
+
+
+def test_torch_sort_operator_float_keys(rsb):
+    # float keys ride on the integer sort through the order-preserving bit transform (torch_op.py)
+    import importlib
+    op = importlib.import_module("radix-sort_b200.torch_op")
+    torch = _torch()
+    rng = np.random.default_rng(22)
+    for np_dt in (np.float32, np.float64):
+        host = (rng.standard_normal(200_000) * 1e4).astype(np_dt)
+        host[:4] = [0.0, -0.0, np.inf, -np.inf]
+        values, indices = op.sort(torch.from_numpy(host.copy()).cuda())
+        torch.cuda.synchronize()
+        got = values.cpu().numpy()
+        assert np.array_equal(got, np.sort(host)) and np.array_equal(host[indices.cpu().numpy()], got)

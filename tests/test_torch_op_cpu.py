@@ -83,10 +83,31 @@ def test_sorter_cache_grows_and_is_reused(op):
     assert all(s.closed for s in _FakeSorter.created)
 
 
+def test_float_keys_total_order(op):
+    ts = op.TorchSorter(0, backend=_FakeBackend())
+    rng = np.random.default_rng(3)
+    for dt, np_dt in ((torch.float32, np.float32), (torch.float64, np.float64)):
+        host = rng.standard_normal(5000).astype(np_dt) * np_dt(1e3)
+        host[:8] = [0.0, -0.0, np.inf, -np.inf, 1.0, -1.0, np.finfo(np_dt).tiny, -np.finfo(np_dt).max]
+        keys = torch.from_numpy(host.copy())
+        values, indices = ts.sort(keys)
+        assert values.dtype == dt
+        got = values.numpy()
+        assert np.array_equal(np.sort(host), got)                      # no NaNs here: numeric order == total order
+        assert np.array_equal(host[indices.numpy()], got)
+        z = np.flatnonzero(got == 0.0)
+        assert np.signbit(got[z[0]]) and not np.signbit(got[z[-1]])    # -0.0 before +0.0
+        assert torch.equal(keys, torch.from_numpy(host))               # input untouched
+        with_nan = torch.tensor([1.0, float("nan"), -2.0, float("inf")], dtype=dt)
+        v, _ = ts.sort(with_nan)
+        assert torch.isnan(v[-1]) and v[0].item() == -2.0 and torch.isinf(v[-2])
+    ts.close()
+
+
 def test_argument_checks(op):
     ts = op.TorchSorter(0, backend=_FakeBackend())
     with pytest.raises(TypeError):
-        ts.sort(torch.zeros(4, dtype=torch.float32))
+        ts.sort(torch.zeros(4, dtype=torch.float16))
     with pytest.raises(ValueError):
         ts.sort(torch.zeros((2, 2), dtype=torch.int32))
     with pytest.raises(ValueError):
