@@ -10,6 +10,7 @@ float32 / float64 keys (additive: the reference excludes float
 usual order-preserving bit transform -- flip the magnitude bits of negative values, then sort as signed integers --
 applied with two elementwise torch ops around the integer sort; the C ABI itself stays integer-only.  Order is the
 IEEE total order of the bit patterns: -NaN < -inf < ... < -0.0 < +0.0 < ... < +inf < +NaN.
+int16 / uint16 keys are widened to 32 bits and sorted on bits 0..15 only (two passes instead of four).
 
 There is no CPU fallback: a tensor that is not on a CUDA device, or a missing ``librsb200.so``, raises.
 The reference has no counterpart (its user entry is examples/basic_sort/basic_sort.cpp:24-139, host buffers only).
@@ -22,6 +23,7 @@ from . import capi
 
 _KEY_OF_DTYPE = {"torch.int32": "i32", "torch.int64": "i64", "torch.uint32": "u32", "torch.uint64": "u64"}
 _INT_OF_FLOAT = {"torch.float32": ("int32", 31), "torch.float64": ("int64", 63)}
+_BIAS_OF_NARROW = {"torch.int16": 1 << 15, "torch.uint16": 0}   # 16-bit keys: widened, biased to 0..65535, two passes
 
 
 def _float_to_ordered(bits, sign_shift: int):
@@ -65,8 +67,14 @@ class TorchSorter:
             entry = self._sorters[(key_type, cuda_stream)] = (self.backend.make_sorter(key_type, capacity), capacity)
         return entry[0]
 
-    def sort(self, keys, return_indices: bool = True):
+    def sort(self, keys, return_indices: bool = True, end_bit: int | None = None):
         import torch
+        bias = _BIAS_OF_NARROW.get(str(keys.dtype))
+        if bias is not None:
+            if keys.dim() != 1 or not keys.is_contiguous():
+                raise ValueError("keys must be a contiguous 1-D tensor")
+            wide, indices = self.sort(keys.to(torch.int32) + bias, return_indices, end_bit=16)   # digits of bits 0..15 only
+            return (wide - bias).to(keys.dtype), indices
         as_float = _INT_OF_FLOAT.get(str(keys.dtype))
         if as_float is not None:
             if keys.dim() != 1 or not keys.is_contiguous():
@@ -76,7 +84,7 @@ class TorchSorter:
             return _float_to_ordered(ordered, sign_shift).view(keys.dtype), indices
         key_type = _KEY_OF_DTYPE.get(str(keys.dtype))
         if key_type is None:
-            raise TypeError(f"unsupported key dtype {keys.dtype}: int32, int64, uint32, uint64, float32, float64")
+            raise TypeError(f"unsupported key dtype {keys.dtype}: (u)int16, (u)int32, (u)int64, float32, float64")
         if keys.dim() != 1 or not keys.is_contiguous():
             raise ValueError("keys must be a contiguous 1-D tensor")
         if self.backend.__class__ is _NativeBackend and not keys.is_cuda:
@@ -97,9 +105,9 @@ class TorchSorter:
                 vin = torch.arange(n, dtype=torch.int32, device=keys.device)
                 vbuf = [torch.empty_like(vin), torch.empty_like(vin)]
                 r = sorter.sort_device(stream, keys.data_ptr(), kbuf[0].data_ptr(), kbuf[1].data_ptr(), n,
-                                       vin.data_ptr(), vbuf[0].data_ptr(), vbuf[1].data_ptr())
+                                       vin.data_ptr(), vbuf[0].data_ptr(), vbuf[1].data_ptr(), 0, end_bit)
                 return kbuf[r], vbuf[r]
-            r = sorter.sort_device(stream, keys.data_ptr(), kbuf[0].data_ptr(), kbuf[1].data_ptr(), n)
+            r = sorter.sort_device(stream, keys.data_ptr(), kbuf[0].data_ptr(), kbuf[1].data_ptr(), n, None, None, None, 0, end_bit)
             return kbuf[r], None
 
     def close(self):

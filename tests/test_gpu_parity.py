@@ -580,3 +580,16 @@ def test_torch_sort_operator_float_keys(rsb):
         torch.cuda.synchronize()
         got = values.cpu().numpy()
         assert np.array_equal(got, np.sort(host)) and np.array_equal(host[indices.cpu().numpy()], got)
+
+
+def test_torch_sort_operator_int16_keys(rsb):
+    # 16-bit keys: widened and sorted on bits 0..15 only, i.e. two onesweep passes (torch_op.py)
+    import importlib
+    op = importlib.import_module("radix-sort_b200.torch_op")
+    torch = _torch()
+    host = np.random.default_rng(23).integers(-32768, 32767, size=500_000, dtype=np.int16, endpoint=True)
+    values, indices = op.sort(torch.from_numpy(host.copy()).cuda())
+    torch.cuda.synchronize()
+    order = np.argsort(host, kind="stable")
+    assert values.dtype == torch.int16
+    assert np.array_equal(values.cpu().numpy(), host[order]) and np.array_equal(indices.cpu().numpy().astype(np.int64), order)

@@ -26,10 +26,12 @@ class _FakeSorter:
     def _view(self, ptr, n, dt):
         return np.ctypeslib.as_array((ctypes.c_uint8 * (n * np.dtype(dt).itemsize)).from_address(ptr)).view(dt)
 
-    def sort_device(self, stream, d_in, d_buf0, d_buf1, n, d_vin=None, d_vbuf0=None, d_vbuf1=None):
-        assert not self.closed and n <= self.capacity
+    def sort_device(self, stream, d_in, d_buf0, d_buf1, n, d_vin=None, d_vbuf0=None, d_vbuf1=None, begin_bit=0, end_bit=None):
+        assert not self.closed and n <= self.capacity and begin_bit == 0
         keys = self._view(d_in, n, self.np_dt)
-        order = np.argsort(keys, kind="stable")
+        bits = self.np_dt().itemsize * 8 if end_bit is None else end_bit
+        digits = keys if end_bit is None else (keys.astype(np.int64) & ((1 << bits) - 1))   # only bits [0, end_bit) order the keys
+        order = np.argsort(digits, kind="stable")
         self._view(d_buf1, n, self.np_dt)[:] = keys[order]
         self._view(d_buf0, n, self.np_dt)[:] = 0
         if d_vin is not None:
@@ -101,6 +103,22 @@ def test_float_keys_total_order(op):
         with_nan = torch.tensor([1.0, float("nan"), -2.0, float("inf")], dtype=dt)
         v, _ = ts.sort(with_nan)
         assert torch.isnan(v[-1]) and v[0].item() == -2.0 and torch.isinf(v[-2])
+    ts.close()
+
+
+def test_16_bit_keys_two_passes(op):
+    ts = op.TorchSorter(0, backend=_FakeBackend())
+    rng = np.random.default_rng(4)
+    for dt, np_dt in ((torch.int16, np.int16), (torch.uint16, np.uint16)):
+        info = np.iinfo(np_dt)
+        host = rng.integers(info.min, info.max, size=20_000, dtype=np_dt, endpoint=True)
+        host[:2] = [info.min, info.max]
+        keys = torch.from_numpy(host.view(np.int16).copy()).view(dt)
+        values, indices = ts.sort(keys)
+        assert values.dtype == dt
+        order = np.argsort(host, kind="stable")
+        assert np.array_equal(values.view(torch.int16).numpy().view(np_dt), host[order])
+        assert np.array_equal(indices.numpy().astype(np.int64), order)
     ts.close()
 
 
