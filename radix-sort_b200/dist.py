@@ -64,6 +64,14 @@ class CudaOps:
         self.stream.sync()
         return pos.cpu().numpy()
 
+    def lower_bound_device(self, sorted_keys, queries):
+        """Same search with the queries (key storage dtype) and the result (int64) staying on the device.  Enqueued on
+        self.stream, which must wrap the torch stream the caller's tensor ops run on (as bench.py and the tools do)."""
+        pos = self.torch.empty(queries.numel(), dtype=self.torch.int64, device=queries.device)
+        self.ctx.lower_bound(self.stream, self.key_type, sorted_keys.data_ptr(), sorted_keys.numel(), queries.data_ptr(),
+                             queries.numel(), pos.data_ptr())
+        return pos
+
     # ---- peer-memory exchange (NVLink, CUDA IPC) ---------------------------------------------------------
     def enable_p2p(self, dist, capacity_keys: int, group=None):
         """Allocate the two local-sort buffers with plain cudaMalloc, export them through CUDA IPC and map every
@@ -201,6 +209,79 @@ def plan_exchange(sorted_keys, ops, dist, key_type: str, group=None, device=None
     return cuts, t_recv.cpu().numpy()
 
 
+def plan_exchange_device(sorted_keys, ops, dist, key_type: str, group=None, device=None):
+    """plan_exchange with the refinement state kept on the device: same splitters, same cuts, no host round trip.
+
+    The host version pays a device->host->device round trip for every lower-bound query set and every all-reduce
+    (about ten per plan; 1.9 ms of the 25 ms step at 8 GPUs).  Here the queries of a round are built from the previous
+    round's result with a handful of tiny tensor ops, `ops.lower_bound_device` (rs_lower_bound_device) reads them where
+    they are, and the collectives run on the device tensors.  Returns the cuts as an int64 DEVICE tensor of world+1
+    entries; the caller reads it back together with whatever else it gathers (one synchronisation per sort).
+    Ordered-unsigned key values are carried as int64 bit patterns; 64-bit keys rely on two's complement wrap-around.
+    """
+    import torch
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    bits, sign = _key_bits(key_type), _sign(key_type)
+    n_local = int(sorted_keys.numel())
+    dev = device if device is not None else sorted_keys.device
+    i64 = dict(dtype=torch.int64, device=dev)
+    if world == 1:
+        return torch.tensor([0, n_local], **i64)
+    mask = (1 << bits) - 1 if bits < 64 else -1           # as an int64 scalar
+    sign64 = sign if sign < (1 << 63) else sign - (1 << 64)
+
+    def positions(ordered, top_flags):
+        """lower bound of ordered-unsigned values in the local shard; entries flagged in top_flags mean 2^bits"""
+        vals = (ordered & mask) ^ sign64                  # key bit patterns
+        if bits == 32:
+            vals = ((vals ^ 0x80000000) - 0x80000000).to(torch.int32)   # the low 32 bits as an int32 bit pattern
+        pos = ops.lower_bound_device(sorted_keys, vals.contiguous())
+        return torch.where(top_flags, torch.full_like(pos, n_local), pos)
+
+    w = world - 1
+    ranks = torch.arange(1, world, **i64)
+    prefix = torch.zeros(w, **i64)    # per splitter: ordered-unsigned key bits resolved so far
+    below = torch.zeros(w, **i64)     # per splitter: number of keys globally below `prefix`
+    targets = None
+    resolved, level = 0, 0
+    while resolved < bits:
+        width = min(LEVEL_BITS, bits - resolved)
+        fan = 1 << width
+        shift = bits - resolved - width
+        steps = torch.arange(fan + 1, **i64) << shift
+        bases = prefix[:1] * 0 if level == 0 else prefix           # level 0: one histogram serves every splitter
+        q = bases[:, None] + steps[None, :]                        # [len(bases), fan + 1]
+        # the last boundary of a row is base + fan << shift, a positive multiple of fan << shift: it is 2^bits itself
+        # exactly when its low `bits` bits are zero
+        top = torch.zeros_like(q, dtype=torch.bool)
+        top[:, -1] = (q[:, -1] & mask) == 0
+        pos = positions(q.reshape(-1), top.reshape(-1)).view(q.shape)
+        counts = (pos[:, 1:] - pos[:, :-1]).contiguous()
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)  # global sub-range counts
+        if level == 0:
+            targets = (ranks * counts[0].sum()) // world            # global rank of the first key of rank j
+            counts = counts.expand(w, fan)
+        cum = torch.cat((below[:, None], below[:, None] + torch.cumsum(counts, dim=1)), dim=1)   # [w, fan + 1]
+        b = (torch.searchsorted(cum, targets[:, None].contiguous(), right=True) - 1).clamp_(0, fan - 1)   # cum[b] <= target < cum[b+1]
+        prefix = prefix + (b[:, 0] << shift)
+        below = torch.gather(cum, 1, b)[:, 0]
+        resolved += width
+        level += 1
+    # prefix[j] is now an exact key value v_j; the copies of v_j are split by count, in rank order
+    pair = torch.stack((prefix, prefix + 1), dim=1)                # v and v + 1 (2^bits when v is the largest key)
+    top = torch.zeros_like(pair, dtype=torch.bool)
+    top[:, 1] = (pair[:, 1] & mask) == 0
+    pos = positions(pair.reshape(-1), top.reshape(-1)).view(w, 2)
+    lb, eq_local = pos[:, 0], pos[:, 1] - pos[:, 0]
+    parts = [torch.empty_like(eq_local) for _ in range(world)]
+    dist.all_gather(parts, eq_local.contiguous(), group=group)
+    before_me = torch.stack(parts)[:rank].sum(dim=0) if rank else torch.zeros_like(eq_local)
+    share = torch.minimum((targets - below - before_me).clamp_(min=0), eq_local)   # my copies that belong to ranks <= j
+    cuts = torch.cat((torch.zeros(1, **i64), lb + share, torch.full((1,), n_local, **i64)))
+    return torch.cummax(cuts, dim=0).values   # equal splitters (heavy duplicates) keep the cuts monotone
+
+
 def distributed_sort(keys, ops, dist, key_type: str, scratch=None, group=None):
     """Sort the union of all ranks' `keys`; returns this rank's slice of the global order (device tensor).
 
@@ -257,10 +338,14 @@ def _distributed_sort_p2p(keys, ops, dist, key_type: str, s, group):
     sorted_local = RawBuf(ops.p2p_local[sel], n_local, device=keys.device)
     mark("local sort")
     # 2. exact splitters (all-reduces inside: every peer's local sort is complete once they return)
-    cuts, _ = plan_exchange(sorted_local, ops, dist, key_type, group=group, device=keys.device, need_recv_counts=False)
+    if os.environ.get("RSB200_DEVICE_SPLITTERS") == "1":   # opt-in until it has been timed on the GPU box
+        cuts_dev = plan_exchange_device(sorted_local, ops, dist, key_type, group=group, device=keys.device)
+        mine = torch.cat((cuts_dev, torch.tensor([sel], dtype=torch.int64, device=keys.device)))
+    else:
+        cuts, _ = plan_exchange(sorted_local, ops, dist, key_type, group=group, device=keys.device, need_recv_counts=False)
+        mine = torch.from_numpy(np.concatenate((cuts, [sel])).astype(np.int64)).to(keys.device)
     mark("splitters")
     # 3. everybody learns everybody's cut positions and buffer selector
-    mine = torch.from_numpy(np.concatenate((cuts, [sel])).astype(np.int64)).to(keys.device)
     parts = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(parts, mine, group=group)
     table = torch.stack(parts).cpu().numpy()  # [source][world+1 cuts, sel], one device->host copy

@@ -43,6 +43,12 @@ class NumpyOps:
         return np.searchsorted(self._view(sorted_keys), q, side="left").astype(np.int64)
 
 
+    def lower_bound_device(self, sorted_keys, queries):
+        """queries: tensor of key bit patterns in the storage dtype; result: int64 tensor (the device-side planner's op)"""
+        q = queries.numpy().view(self.np_dt)
+        return torch.from_numpy(np.searchsorted(self._view(sorted_keys), q, side="left").astype(np.int64))
+
+
 def _make_shard(case, key_type, rank, world, n):
     dt = {"u32": np.uint32, "i32": np.int32, "u64": np.uint64, "i64": np.int64}[key_type]
     rng = np.random.default_rng(1000 + rank)
@@ -51,6 +57,10 @@ def _make_shard(case, key_type, rank, world, n):
         return rng.integers(info.min, info.max, size=n, dtype=dt, endpoint=True)
     if case == "zeros":
         return np.zeros(n, dtype=dt)
+    if case == "maxes":  # every key is the largest value: the splitter's successor is 2^bits itself
+        return np.full(n, info.max, dtype=dt)
+    if case == "ends":   # only the smallest and the largest value, and one rank holds nothing
+        return np.empty(0, dtype=dt) if rank == 0 else np.where(rng.integers(0, 2, size=n) == 0, info.min, info.max).astype(dt)
     if case == "few":  # heavy duplicates: ties must be split by count
         return rng.integers(0, 3, size=n).astype(dt)
     if case == "range":  # global range, sharded contiguously
@@ -75,6 +85,11 @@ def _worker(rank, world, port, key_type, cases, n, out_dir):
             shard = _make_shard(case, key_type, rank, world, n)
             t = torch.from_numpy(shard.view(np.int32 if shard.itemsize == 4 else np.int64).copy())
             out = dsort.distributed_sort(t, ops, dist, key_type)
+            # the device-side planner must produce exactly the host planner's cuts
+            srt = torch.from_numpy(np.sort(shard).view(np.int32 if shard.itemsize == 4 else np.int64).copy())
+            cuts_host, _ = dsort.plan_exchange(srt, ops, dist, key_type)
+            cuts_dev = dsort.plan_exchange_device(srt, ops, dist, key_type)
+            assert cuts_dev.dtype == torch.int64 and np.array_equal(cuts_dev.numpy(), cuts_host), (case, rank, cuts_host, cuts_dev)
             np.save(os.path.join(out_dir, f"in_{case}_{rank}.npy"), shard)
             np.save(os.path.join(out_dir, f"out_{case}_{rank}.npy"), out.numpy().view(shard.dtype).copy())
     finally:
@@ -91,7 +106,7 @@ def _free_port():
 
 @pytest.mark.parametrize("world,key_type", [(2, "u32"), (3, "i32"), (2, "i64"), (2, "u64")])
 def test_distributed_sort_host_logic(tmp_path, world, key_type):
-    cases = ["uniform", "zeros", "few", "range", "inverted", "skewed"]
+    cases = ["uniform", "zeros", "few", "range", "inverted", "skewed", "maxes", "ends"]
     n = 5000
     mp.spawn(_worker, args=(world, _free_port(), key_type, cases, n, str(tmp_path)), nprocs=world, join=True)
     for case in cases:
