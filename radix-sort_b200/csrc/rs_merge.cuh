@@ -5,10 +5,14 @@
 // four onesweep passes for P = 2 and still cheaper for P = 8 (log2 P levels).  The first level reads its runs
 // straight from PEER memory (CUDA IPC over NVLink): exchange and merge are one kernel.
 //
-//   rs_merge_partition_kernel : one thread per output-tile boundary, merge-path binary search (global loads)
-//   rs_merge_tiles_kernel     : one CTA per output tile of MERGE_TILE keys: load the two input pieces into
-//                               shared memory, per-thread merge-path split, MERGE_ITEMS-way serial merge in
-//                               registers, padded shared-memory transpose, coalesced store
+//   rs_merge_partition_kernel       : one thread per output-tile boundary, merge-path binary search (global loads),
+//                                     in two phases (coarse boundaries, then between neighbours)
+//   rs_merge_tiles_pipelined_kernel : persistent CTAs, one tile of MERGE_TILE outputs at a time: line-aligned 16-byte
+//                                     loads of the next tile in flight while the current one is merged out of shared
+//                                     memory (per-thread merge-path split, MERGE_ITEMS-way serial merge, transpose,
+//                                     coalesced store); jobs of a batch interleaved
+//   rs_merge_tiles_kernel           : the first version (one CTA per tile, 4-byte loads, nothing in flight), kept for
+//                                     A/B runs (RSB200_MERGE_UNPIPELINED=1)
 // Keys only (the distributed configuration is keys-only); order is the key type's (sign bit flipped for signed).
 #pragma once
 #include <cstdint>
