@@ -238,6 +238,7 @@ class Stream:
     def __init__(self, ctx: Context, cuda_stream: int | None = None):
         self.lib, self.ctx = ctx.lib, ctx
         self.handle = C.c_void_p()
+        self.wrapped = cuda_stream          # the foreign cudaStream_t this object wraps, None for an own stream
         if cuda_stream is None:
             _check(self.lib.rs_stream_create(ctx.handle, C.byref(self.handle)))
         else:

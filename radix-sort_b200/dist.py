@@ -65,11 +65,16 @@ class CudaOps:
         return pos.cpu().numpy()
 
     def lower_bound_device(self, sorted_keys, queries):
-        """Same search with the queries (key storage dtype) and the result (int64) staying on the device.  Enqueued on
-        self.stream, which must wrap the torch stream the caller's tensor ops run on (as bench.py and the tools do)."""
+        """Same search with the queries (key storage dtype) and the result (int64) staying on the device.  No host
+        synchronisation when self.stream wraps torch's current stream (as bench.py and the tools set it up)."""
         pos = self.torch.empty(queries.numel(), dtype=self.torch.int64, device=queries.device)
+        same_stream = getattr(self.stream, "wrapped", None) == self.torch.cuda.current_stream().cuda_stream
+        if not same_stream:
+            self.torch.cuda.current_stream().synchronize()   # the queries were produced on torch's stream
         self.ctx.lower_bound(self.stream, self.key_type, sorted_keys.data_ptr(), sorted_keys.numel(), queries.data_ptr(),
                              queries.numel(), pos.data_ptr())
+        if not same_stream:
+            self.stream.sync()
         return pos
 
     # ---- peer-memory exchange (NVLink, CUDA IPC) ---------------------------------------------------------
