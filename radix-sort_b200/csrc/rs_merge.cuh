@@ -20,10 +20,28 @@
 
 namespace rsb {
 
-constexpr int MERGE_THREADS  = 256;
-constexpr int MERGE_ITEMS    = 16;
+// Tile shape of the merge kernels; overridable at compile time for A/B builds (tools/build_variants.sh, EXTRA=-D...).
+#ifndef RS_MERGE_THREADS
+#define RS_MERGE_THREADS 256
+#endif
+#ifndef RS_MERGE_ITEMS
+#define RS_MERGE_ITEMS 16
+#endif
+#ifndef RS_MERGE_MINB32          // resident CTAs per SM the tile kernel is compiled for: 4-byte keys, local runs
+#define RS_MERGE_MINB32 4
+#endif
+#ifndef RS_MERGE_MINB32_DENSE    // 4-byte keys, runs in peer memory
+#define RS_MERGE_MINB32_DENSE 6
+#endif
+#ifndef RS_MERGE_MINB64          // 8-byte keys
+#define RS_MERGE_MINB64 3
+#endif
+constexpr int MERGE_THREADS  = RS_MERGE_THREADS;
+constexpr int MERGE_ITEMS    = RS_MERGE_ITEMS;
 constexpr int MERGE_TILE     = MERGE_THREADS * MERGE_ITEMS;  // 4096 outputs per CTA
 constexpr int MERGE_MAX_JOBS = 8;
+static_assert(MERGE_THREADS % 32 == 0 && (MERGE_ITEMS == 8 || MERGE_ITEMS == 16 || MERGE_ITEMS == 32),
+              "the padded transpose is conflict-free for 8, 16 or 32 items per thread");
 
 template <typename KeyT>
 struct MergeBatch {
@@ -192,7 +210,7 @@ struct MergeSlot {          // per thread
 // when both runs are local (2.56 vs 2.26 ms per 2^30 keys) but it holds 1.5x the bytes in flight, which is what bounds
 // a level whose runs live in peer memory; the host picks it when an input pointer belongs to another device.
 template <typename KeyT, bool DENSE>
-__global__ void __launch_bounds__(MERGE_THREADS, sizeof(KeyT) == 4 ? (DENSE ? 6 : 4) : 3)
+__global__ void __launch_bounds__(MERGE_THREADS, sizeof(KeyT) == 4 ? (DENSE ? RS_MERGE_MINB32_DENSE : RS_MERGE_MINB32) : RS_MERGE_MINB64)
 rs_merge_tiles_pipelined_kernel(const MergeBatch<KeyT> mb_param, const unsigned long long* __restrict__ splits,
                                 const uint32_t max_tiles_per_job) {
     constexpr uint32_t LINE = MERGE_LINE_BYTES / sizeof(KeyT);          // elements per line
@@ -308,7 +326,7 @@ rs_merge_tiles_pipelined_kernel(const MergeBatch<KeyT> mb_param, const unsigned 
         KeyT     ka = sa[ai], kb = sb[bi];
         if constexpr (sizeof(KeyT) == 4) {
             // 4-byte keys: scalar stores into the padded transpose as the merge goes (measured faster than vectors here)
-            KeyT* const wo = so + tid * MERGE_ITEMS + (tid >> 1);      // == merge_pad(tid * MERGE_ITEMS + k) - k
+            KeyT* const wo = so + tid * MERGE_ITEMS + ((tid * MERGE_ITEMS) >> 5);   // == merge_pad(tid * MERGE_ITEMS + k) - k
 #pragma unroll
             for (int k = 0; k < MERGE_ITEMS; ++k) {
                 const bool take_a = (bi >= lb) || (ai < la && ka <= kb);

@@ -391,7 +391,7 @@ def _distributed_sort_p2p(keys, ops, dist, key_type: str, s, group):
 def _merge_tree(ops, key_type, ptrs, counts, buf_x, buf_y, n_total, kb, scratch):
     """Merge the sorted runs (ptr, count) pairwise, level by level, ping-ponging between buf_x and buf_y."""
     import torch
-    tiles_max = (n_total + 4095) // 4096 + 2 * len(ptrs) + 16
+    tiles_max = (n_total + 1023) // 1024 + 2 * len(ptrs) + 16   # enough for any tile shape of the A/B builds (>= 1024 outputs)
     splits = scratch.get("splits")
     if splits is None or splits.numel() < tiles_max:
         splits = torch.empty(tiles_max, dtype=torch.int64, device=buf_x.device)

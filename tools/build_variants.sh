@@ -11,3 +11,6 @@ for cfg in "$@"; do
        -DRS_$1_THREADS=$2 -DRS_$1_KPT=$3 -DRS_$1_MINB=$4 $EXTRA -Xptxas -v -shared -o $out rs_api.cu 2> /tmp/variant_ptxas.log
   echo "$out: $(grep -A2 "ELi$2ELi$3ELi$4ELb1" /tmp/variant_ptxas.log | grep -E 'registers|spill' | sed 's/ptxas info    : //' | tr '\n' ' ' | cut -c1-300)"
 done
+# Merge tile shapes: EXTRA="-DRS_MERGE_THREADS=128 -DRS_MERGE_ITEMS=32 -DRS_MERGE_MINB32=6" tools/build_variants.sh "U32A 512 22 2"
+# (RS_MERGE_MINB32 / RS_MERGE_MINB32_DENSE / RS_MERGE_MINB64 = resident CTAs per SM the tile kernel is compiled for);
+# run with RSB200_LIB=variants/<file>.so python tools/merge_bench.py

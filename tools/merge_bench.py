@@ -34,7 +34,7 @@ def main():
     s.close()
     del bufs, src
     out = torch.empty(n, dtype=tdt, device="cuda")
-    splits = torch.empty(n // 4096 + 64, dtype=torch.int64, device="cuda")
+    splits = torch.empty(n // 1024 + 64, dtype=torch.int64, device="cuda")   # enough for the tile-shape variants too
     # `jobs` independent merges of equal size (slices of the two sorted runs are sorted runs themselves)
     job_list = [(runs[0].data_ptr() + j * per * kb, per, runs[1].data_ptr() + j * per * kb, per, out.data_ptr() + 2 * j * per * kb)
                 for j in range(jobs)]
