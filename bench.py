@@ -116,7 +116,8 @@ def cpu_reference_gkeys(sample_log2, dataset, iterations):
         ms = (time.perf_counter() - t0) * 1e3 / iterations
         kind = "port"
     return {"value": n / ms / 1e6, "unit": UNIT, "cores": 1, "kind": kind, "host_cores_available": os.cpu_count(),
-            "sample": f"2^{sample_log2} uint32 keys, '{dataset}' dataset (reference generator, seed 0x5EED), "
+            "sample": f"2^{sample_log2} uint32 keys, '{dataset}' dataset (reference generator, "
+                      f"{'its fixed seed_seq' if dataset == 'random' else 'seed 0x5EED'}), "
                       f"{iterations} iterations averaged, RadixSortCPU<uint32_t>::sort, 1 thread",
             "ms_per_sort": ms}
 
@@ -286,6 +287,9 @@ def bench_single(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        # BASELINE.json configs[0], the reference's own CPU-runnable case (2^20 "Random" uint32), beside it
+        c0 = cpu_reference_gkeys(20, "random", 5)
+        line["cpu_baseline"]["configs0"] = {"value": c0["value"], "unit": UNIT, "ms_per_sort": c0["ms_per_sort"], "sample": c0["sample"]}
     print(json.dumps(line), flush=True)
     return 0
 
