@@ -665,9 +665,13 @@ static int merge_runs_typed(rs_context ctx, cudaStream_t st, bool is_signed, int
         cudaGetLastError();  // a pointer the runtime does not know is simply treated as local
         static const char* const force = std::getenv("RSB200_MERGE_DENSE");  // "0" / "1": A/B switch for profiling
         if (force) remote = force[0] == '1';
-        auto kern = remote ? rs_merge_tiles_pipelined_kernel<KeyT, true> : rs_merge_tiles_pipelined_kernel<KeyT, false>;
-        static thread_local int occupancy[2][64] = {};   // per variant and device
-        int& ctas_per_sm = occupancy[remote ? 1 : 0][here & 63];
+        // walk order of the persistent CTAs: the region-strided order (rs_merge_order.h) balances batches whose tiles sit
+        // in few jobs; opt-in until it has been run on the GPU box (the host emulation of the walk is in the CPU tests)
+        static const bool regions = std::getenv("RSB200_MERGE_ORDER_REGIONS") != nullptr;
+        auto kern = regions ? (remote ? rs_merge_tiles_pipelined_kernel<KeyT, true, true> : rs_merge_tiles_pipelined_kernel<KeyT, false, true>)
+                            : (remote ? rs_merge_tiles_pipelined_kernel<KeyT, true, false> : rs_merge_tiles_pipelined_kernel<KeyT, false, false>);
+        static thread_local int occupancy[4][64] = {};   // per variant and device
+        int& ctas_per_sm = occupancy[(remote ? 1 : 0) + (regions ? 2 : 0)][here & 63];
         if (!ctas_per_sm) {
             RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)), RS_CALCULATION_FAILED);
             RS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, MERGE_THREADS, smem), RS_CALCULATION_FAILED);

@@ -18,6 +18,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "rs_merge_order.h"
+
 namespace rsb {
 
 // Tile shape of the merge kernels; overridable at compile time for A/B builds (tools/build_variants.sh, EXTRA=-D...).
@@ -209,7 +211,10 @@ struct MergeSlot {          // per thread
 // DENSE = more resident CTAs with fewer registers each (4-byte keys: 6 x 38 registers instead of 4 x 64).  Slower
 // when both runs are local (2.56 vs 2.26 ms per 2^30 keys) but it holds 1.5x the bytes in flight, which is what bounds
 // a level whose runs live in peer memory; the host picks it when an input pointer belongs to another device.
-template <typename KeyT, bool DENSE>
+// REGIONS selects the walk order: false = slot s -> job s % J, tile s / J (the order every number in profiles/ was
+// measured with; with the grid a multiple of J a CTA never leaves its job, so a batch whose tiles all sit in one job
+// keeps only 1/J of the CTAs busy); true = the region-strided order of rs_merge_order.h, which balances any batch.
+template <typename KeyT, bool DENSE, bool REGIONS>
 __global__ void __launch_bounds__(MERGE_THREADS, sizeof(KeyT) == 4 ? (DENSE ? RS_MERGE_MINB32_DENSE : RS_MERGE_MINB32) : RS_MERGE_MINB64)
 rs_merge_tiles_pipelined_kernel(const MergeBatch<KeyT> mb_param, const unsigned long long* __restrict__ splits,
                                 const uint32_t max_tiles_per_job) {
@@ -220,20 +225,49 @@ rs_merge_tiles_pipelined_kernel(const MergeBatch<KeyT> mb_param, const unsigned 
     constexpr int      ROWS = (MERGE_TILE + 3 * LINE + VEC * MERGE_THREADS - 1) / (VEC * MERGE_THREADS);
     extern __shared__ __align__(16) unsigned char merge_smem[];
     __shared__ MergeBatch<KeyT> mb;
+    __shared__ MergeOrder       order;                      // rs_merge_order.h                        (REGIONS only)
+    __shared__ uint32_t         first_tile[MERGE_MAX_JOBS]; // 32-bit copy of mb.tile_start, < 2^31    (REGIONS only)
     KeyT* const sk = reinterpret_cast<KeyT*>(merge_smem);   // [SK]                          virtual layout, see above
     KeyT* const so = sk + SK;                               // [MERGE_THREADS * SO_STRIDE]   outputs (layout by key size, below)
     const int tid = threadIdx.x;
     if (tid == 0) mb = mb_param;
+    if constexpr (REGIONS) {
+        if (tid == 0) order = merge_order_of(static_cast<uint32_t>(mb_param.tile_start[mb_param.num_jobs]));
+        if (tid < MERGE_MAX_JOBS)   // jobs past num_jobs start at the total, i.e. never own a tile
+            first_tile[tid] = static_cast<uint32_t>(mb_param.tile_start[tid < mb_param.num_jobs ? tid : mb_param.num_jobs]);
+    }
     __syncthreads();
     const uint32_t J = static_cast<uint32_t>(mb.num_jobs);
-    const uint32_t S = J * max_tiles_per_job;               // sequence slots (host guarantees < 2^32)
+    const uint32_t S = REGIONS ? order.slots : J * max_tiles_per_job;   // sequence slots (host guarantees < 2^32)
     const KeyT     sign = mb.sign;
 
+    // slot -> (job, tile within the job)
+    auto locate = [&](uint32_t s, uint32_t& job, uint32_t& lt) {
+        if constexpr (REGIONS) {
+            const uint32_t t = merge_tile_of_slot(order, s);
+            job = 0;
+#pragma unroll
+            for (int j = 1; j < MERGE_MAX_JOBS; ++j)
+                if (t >= first_tile[j]) job = j;     // the owner is the last job that starts at or before t
+            lt = t - first_tile[job];
+        } else {
+            job = s % J;
+            lt  = s / J;
+        }
+    };
+    // does slot s name an existing tile?
+    auto exists = [&](uint32_t s) {
+        if constexpr (REGIONS) {
+            return merge_tile_of_slot(order, s) < order.tiles;
+        } else {
+            const uint32_t job = s % J, lt = s / J;
+            return lt < static_cast<uint32_t>(mb.tile_start[job + 1] - mb.tile_start[job]);
+        }
+    };
     // next slot >= s (stepping by the grid) that names an existing tile; S if none
     auto seek = [&](uint32_t s) {
         while (s < S) {
-            const uint32_t job = s % J, lt = s / J;
-            if (lt < static_cast<uint32_t>(mb.tile_start[job + 1] - mb.tile_start[job])) break;
+            if (exists(s)) break;
             if (S - s <= gridDim.x) { s = S; break; }
             s += gridDim.x;
         }
@@ -242,12 +276,14 @@ rs_merge_tiles_pipelined_kernel(const MergeBatch<KeyT> mb_param, const unsigned 
     auto advance = [&](uint32_t s) { return (S - s <= gridDim.x) ? S : seek(s + gridDim.x); };
     // the two split words of slot s
     auto load_splits = [&](uint32_t s, unsigned long long& s0, unsigned long long& s1) {
-        const uint32_t job = s % J, lt = s / J;
+        uint32_t job, lt;
+        locate(s, job, lt);
         const unsigned long long g = mb.tile_start[job] + lt + job;
         s0 = splits[g]; s1 = splits[g + 1];
     };
     auto make_slot = [&](uint32_t s, unsigned long long a0, unsigned long long a1) {
-        const uint32_t job = s % J, lt = s / J;
+        uint32_t job, lt;
+        locate(s, job, lt);
         const unsigned long long total = mb.na[job] + mb.nb[job];
         const unsigned long long d0 = static_cast<unsigned long long>(lt) * MERGE_TILE;
         const unsigned long long d1 = (d0 + MERGE_TILE < total) ? d0 + MERGE_TILE : total;

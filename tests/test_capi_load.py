@@ -74,3 +74,18 @@ def test_bench_reference_arm_line():
     assert line["metric"] == "Gkeys/s sorting 2^28 uint32 keys" and 0 < line["value"] < 1.0
     assert line["cpu_baseline"]["cores"] == 1 and line["cpu_baseline"]["kind"] in ("reference", "port")
     assert line["e2e"] == {"value": line["value"], "unit": "Gkeys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_merge_tile_order_covers_every_tile_once():
+    # the region-strided order in which the merge CTAs can walk a batch (csrc/rs_merge_order.h, the REGIONS
+    # instantiation of the tile kernel; opt-in until it has run on hardware), checked on the host:
+    # the C++ function itself (bijection, few empty slots) and the kernel's seek/advance/locate walk for many job shapes
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "merge_order_check")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(root, "tests", "cpp"), "merge_order_check"], check=True, capture_output=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "merge order ok" in out.stdout, out.stdout + out.stderr
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "merge_order_emulation.py")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "every tile exactly once" in out.stdout, out.stdout + out.stderr
