@@ -33,13 +33,16 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "Gkeys/s sorting 2^28 uint32 keys"
+METRIC_DIST = "Gkeys/s sorting 2^33 uint32 keys distributed over the GPUs of one box"
 UNIT = "Gkeys/s"
 LOG2_SINGLE = 28
 LOG2_DIST_TOTAL = 33
 KEY_TYPE = "u32"
 KEY_BYTES = 4
 PASSES = 4
-CPU_SAMPLE_LOG2 = 24          # bounded CPU sample: 2^24 keys of the same workload
+CPU_SAMPLE_LOG2 = 24          # cpu_baseline leg of our own arm: bounded sample, 2^24 keys of the same workload
+REFERENCE_BUDGET_S = 100.0    # --impl reference: whole 2^28-key sorts until K steps or this many seconds (>= 1 sort)
+NVLINK_PEER_READ_GBS = 672.0  # measured both-ways peer-read rate of one GPU (tools/peerbw.cu, profiles/r1f_peerbw_aligned.txt)
 FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -97,29 +100,39 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_gkeys(sample_log2, dataset, iterations):
-    """RadixSortCPU<uint32_t>::sort on a 2^sample_log2 prefix of the workload's input, averaged like
-    _NUM_PERFORMANCE_ITERATIONS (src/CRadixSortTask.cpp:203-221).  Single host thread."""
-    import numpy as np
+def cpu_reference_gkeys(sample_log2, dataset, iterations, budget_s=None):
+    """RadixSortCPU<uint32_t>::sort on the first 2^sample_log2 keys of the workload's input (all of it for 28), averaged
+    like _NUM_PERFORMANCE_ITERATIONS (src/CRadixSortTask.cpp:203-221).  Single host thread: the reference is
+    single-threaded.  With budget_s, sorts are timed one at a time until `iterations` or the budget is reached."""
     from oracle import Oracle, Reference, have_reference
     n = 1 << sample_log2
     ora = Oracle()
     data = ora.dataset(dataset, KEY_TYPE, n, 0x5EED)
-    if have_reference():
-        ref = Reference()
-        ms = ref.time_radix_sort_cpu_ms(data, KEY_TYPE, iterations)
-        kind = "reference"
-    else:
+    ref = Reference() if have_reference() else None
+    kind = "reference" if ref is not None else "port"
+
+    def sort_ms(k):
+        if ref is not None:
+            return ref.time_radix_sort_cpu_ms(data, KEY_TYPE, k) * k
         t0 = time.perf_counter()
-        for _ in range(iterations):
+        for _ in range(k):
             ora.radix_sort_cpu(data, KEY_TYPE)
-        ms = (time.perf_counter() - t0) * 1e3 / iterations
-        kind = "port"
+        return (time.perf_counter() - t0) * 1e3
+
+    if budget_s is None:
+        done, total_ms = iterations, sort_ms(iterations)
+    else:
+        done, total_ms = 0, 0.0
+        while done < iterations and (done == 0 or total_ms * 1e-3 * (done + 1) / done < budget_s):
+            total_ms += sort_ms(1)
+            done += 1
+    ms = total_ms / done
     return {"value": n / ms / 1e6, "unit": UNIT, "cores": 1, "kind": kind, "host_cores_available": os.cpu_count(),
             "sample": f"2^{sample_log2} uint32 keys, '{dataset}' dataset (reference generator, "
                       f"{'its fixed seed_seq' if dataset == 'random' else 'seed 0x5EED'}), "
-                      f"{iterations} iterations averaged, RadixSortCPU<uint32_t>::sort, 1 thread",
-            "ms_per_sort": ms}
+                      f"{done} iteration{'s' if done != 1 else ''} averaged, RadixSortCPU<uint32_t>::sort, 1 thread "
+                      f"(the reference is single-threaded; the host has {os.cpu_count()} cores)",
+            "ms_per_sort": ms, "iterations": done}
 
 
 def run_reference_arm(args):
@@ -128,18 +141,23 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     dataset = args.dataset
-    # warm-up + K timed steps; each step = one bounded-sample sort (2^24 keys takes ~2-3 s)
+    # warm-up (a small sort), then whole sorts of the N=1 workload itself -- all 2^28 keys, one step = one sort (about
+    # half a minute each) -- until K steps or REFERENCE_BUDGET_S; the line says how many were timed.  For N > 1 the
+    # workload is 2^33 keys (32 GiB): out of reach of a bounded CPU step, so the same 2^28-key sort is the sample.
     for _ in range(min(args.warmup, 1)):
         cpu_reference_gkeys(20, dataset, 1)
-    res = cpu_reference_gkeys(CPU_SAMPLE_LOG2, dataset, max(1, args.steps))
-    n_total = (1 << LOG2_SINGLE) if args.gpus == 1 else (1 << LOG2_DIST_TOTAL)
+    res = cpu_reference_gkeys(args.log2n, dataset, max(1, args.steps), budget_s=REFERENCE_BUDGET_S)
+    n_total = (1 << args.log2n) if args.gpus == 1 else (1 << args.log2n_total)
+    note = ("CPU reference timed on the whole workload: " if args.gpus == 1 else
+            "CPU reference timed on a bounded sample (2^28 of the 2^33 keys): ") + res["sample"]
     line = {
-        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_sort"], "higher_is_better": True,
+        "impl": "reference", "metric": METRIC if args.gpus == 1 else METRIC_DIST, "value": res["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": res["iterations"], "steps_requested": args.steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": res["ms_per_sort"], "higher_is_better": True,
         "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": workload_name(args.gpus, dataset), "keys_total": n_total,
-                   "note": "CPU reference timed on a bounded sample of the workload: " + res["sample"]},
-        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "config": {"workload": workload_name(args.gpus, dataset), "keys_total": n_total, "keys_timed_per_step": 1 << args.log2n,
+                   "note": note},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores_available")},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -153,6 +171,52 @@ def workload_name(gpus, dataset):
     return (f"2^{LOG2_DIST_TOTAL} uint32 keys total, keys-only, '{dataset}' dataset generated per shard on the devices, "
             f"{gpus}xB200: local onesweep + MSD splitter all-reduce + exchange over NVLink + final local sort "
             f"(BASELINE.json configs[4])")
+
+
+def measure_other_config(rsb, torch, ctx, st, key_type, with_perm, n, steps, peak):
+    """Device-resident sort of n keys of another key type / payload (BASELINE.json configs[2], [3] and the added
+    key types): Gkeys/s, algorithmic bytes per key and the fraction of the HBM roofline, same timing rules as the
+    headline (warm-ups, CUDA events, inputs far larger than L2)."""
+    kb = rsb.key_dtype(key_type).itemsize
+    tdt = {2: torch.int16, 4: torch.int32, 8: torch.int64}[kb]
+    d_in = torch.empty(n, dtype=tdt, device="cuda")
+    bufs = [torch.empty(n, dtype=tdt, device="cuda") for _ in range(2)]
+    vin = torch.arange(n, dtype=torch.int32, device="cuda") if with_perm else None
+    vb = [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(2)] if with_perm else [None, None]
+    ctx.fill_dataset(st, key_type, "uniform", d_in.data_ptr(), n, seed=0x5EED)
+    sorter = rsb.Sorter(ctx, key_type, n, rsb.RS_NO_KEY_BUFFERS)
+
+    def once():
+        return sorter.sort_device(st, d_in.data_ptr(), bufs[0].data_ptr(), bufs[1].data_ptr(), n,
+                                  vin.data_ptr() if with_perm else None, vb[0].data_ptr() if with_perm else None,
+                                  vb[1].data_ptr() if with_perm else None)
+
+    for _ in range(3):
+        r = once()
+    torch.cuda.synchronize()
+    l0 = sorter.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        once()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = sorter.launch_count - l0
+    chk = ctx.check(st, key_type, bufs[r].data_ptr(), n)
+    if chk["unordered"] != 0:
+        raise RuntimeError(f"bench: {key_type} output is not sorted")
+    if with_perm:
+        res = ctx.check_permutation(st, key_type, d_in.data_ptr(), bufs[r].data_ptr(), vb[r].data_ptr(), n)
+        if res != {"mismatches": 0, "unstable": 0}:
+            raise RuntimeError(f"bench: {key_type} permutation is not the stable sorting permutation")
+    sorter.close()
+    passes = kb
+    bpk = kb + passes * 2 * (kb + (4 if with_perm else 0))
+    gbs = bpk * n / (ms * 1e-3) / 1e9
+    return {"key_type": key_type, "index_payload": bool(with_perm), "keys": n, "dataset": "uniform", "ms_per_sort": round(ms, 4),
+            "gkeys_s": round(n / ms / 1e6, 3), "passes": passes, "algorithmic_bytes_per_key": bpk,
+            "achieved_gbs": round(gbs, 1), "roofline_frac": round(gbs / peak, 4)}, launches
 
 
 def bench_single(args):
@@ -205,6 +269,17 @@ def bench_single(args):
             launches = sorter.launch_count - l0
             rt_head = sorter.runtimes()
 
+    # ---- BASELINE.json configs[2] and [3] (key + index, signed and 64-bit keys) and the added key types, same size ----
+    peak, peak_src = measured_hbm_peak()
+    other_configs, other_launches = [], 0
+    if not args.no_other:
+        del bufs[:]
+        other_steps = max(3, min(args.steps, 10))
+        for key_type, with_perm in (("u32", True), ("i32", False), ("u64", False), ("i64", False), ("u64", True), ("f32", False), ("u16", False)):
+            res, nl = measure_other_config(rsb, torch, ctx, st, key_type, with_perm, n, other_steps, peak)
+            other_configs.append(res)
+            other_launches += nl
+        bufs = [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(2)]
     clocks = sampler.finish()
 
     # ---- end to end through the reference-facing calls with pinned HOST buffers ---------------------------
@@ -234,10 +309,14 @@ def bench_single(args):
     e2e_run(e2e_steps)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    # every lane's host result: sorted AND the same multiset as the host input (a stale or partial download fails)
+    want = ctx.check(st, KEY_TYPE, d_in.data_ptr(), n)
     for _, _, hout in lanes:
-        out = hout.array
-        if not bool((out[1:] >= out[:-1]).all()):
-            raise RuntimeError("bench: e2e output is not sorted")
+        bufs[0].copy_(torch.from_numpy(hout.array.view(np.int32)))
+        torch.cuda.synchronize()
+        got = ctx.check(st, KEY_TYPE, bufs[0].data_ptr(), n)
+        if got["unordered"] != 0 or any(got[k] != want[k] for k in ("sum", "hash_sum", "hash_xor")):
+            raise RuntimeError("bench: e2e output is not the sorted input")
     # the plain sequential call sequence of one batch (what RadixSortGPU::uploadData/calculate/downloadData do)
     srt, stream, hout = lanes[0]
     t0 = time.perf_counter()
@@ -250,12 +329,13 @@ def bench_single(args):
            "api": "rs_sorter_upload -> rs_sorter_sort -> rs_sorter_download_async on three sorters/streams "
                   "(batch i+2 uploads while batch i+1 sorts and batch i downloads), pinned host buffers",
            "timing": "host wall clock between device synchronisations",
+           "verified": "each lane's downloaded buffer: sorted, and multiset fingerprint equal to the host input's",
+           "input": "every step uploads the same pinned 1 GiB host buffer (the workload), and downloads 1 GiB",
            "single_batch_sequential_ms": seq_ms, "single_batch_sequential_gkeys_s": n / seq_ms / 1e6}
     for srt, stream, hout in lanes:
         srt.close(); stream.close(); hout.close()
 
     # ---- roofline of the dominant kernel (one onesweep pass) ----------------------------------------------
-    peak, peak_src = measured_hbm_peak()
     pass_ms = rt_head["time_reorder"]["avg"] / PASSES
     alg_bytes = 2 * KEY_BYTES * n
     achieved = alg_bytes / (pass_ms * 1e-3) / 1e9
@@ -265,7 +345,7 @@ def bench_single(args):
             traffic = json.load(f).get("onesweep_u32_keys_2^28_dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "rs_onesweep_kernel<u32, keys-only> (one pass)", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": "rs_sweep_kernel<u32, keys-only> (one onesweep pass)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": pass_ms,
                 "whole_sort": {"algorithmic_bytes": (KEY_BYTES + PASSES * 2 * KEY_BYTES) * n,
@@ -281,12 +361,15 @@ def bench_single(args):
         "config": {"workload": workload_name(1, args.dataset), "keys": n, "passes": PASSES, "digit_bits": 8,
                    "l2": "inputs (1 GiB per buffer) are larger than the 126 MB L2; no flush needed",
                    "datasets_gkeys_s": per_dataset, "datasets_passes_skipped": skipped,
+                   "other_configs": other_configs,
+                   "verified": "timed loops: output sorted (device check, every dataset and configuration; key+index "
+                               "configurations also the stable permutation); exact compares live in tests/",
                    "skip_note": "a pass whose digit is equal for all keys is the identity and is skipped on the device; "
                                 "Gkeys/s is keys sorted per second, not bytes moved"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
     }
     if cpu is not None:
-        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores_available")}
         # BASELINE.json configs[0], the reference's own CPU-runnable case (2^20 "Random" uint32), beside it
         c0 = cpu_reference_gkeys(20, "random", 5)
         line["cpu_baseline"]["configs0"] = {"value": c0["value"], "unit": UNIT, "ms_per_sort": c0["ms_per_sort"], "sample": c0["sample"]}
@@ -328,6 +411,17 @@ def bench_distributed(args):
                 ops.close()
                 ops = dsort.CudaOps(rsb, ctx, st, KEY_TYPE, n_local + n_local // 8 + (1 << 20))
             exchange = "nccl"
+    # ---- exact parity on THIS box before anything is timed: 2^22 keys, 4 key types x 5 datasets against numpy,
+    #      through the same exchange / final step (tools/dist_check.py); a mismatch fails the bench -------------------
+    from tools.dist_check import run_checks
+    parity_log = []
+    parity_cases, parity_failures = run_checks(rsb, dsort, dist, torch, ctx, st, 1 << 22, exchange, args.final, log=parity_log.append)
+    if rank == 0:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"dist_parity_n{world}.txt"), "w") as f:
+            f.write("\n".join(parity_log) + f"\n{parity_cases} cases, {parity_failures} failures\n")
+    if parity_failures:
+        raise RuntimeError(f"bench: distributed sort failed exact parity in {parity_failures} of {parity_cases} cases")
     shard = ops.empty(n_local)
     scratch = {k: ops.empty(cap) for k in (("recv", "c") if exchange == "p2p" else ("a", "b", "recv", "c"))}
     ctx.fill_dataset(st, KEY_TYPE, args.dataset, shard.data_ptr(), n_local, seed=0x5EED,
@@ -361,6 +455,62 @@ def bench_distributed(args):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     clocks = sampler.finish() if sampler else None
+
+    def verify(out, before):
+        """locally sorted, boundaries ordered across ranks, multiset preserved, exact balance (collectives inside)"""
+        after = ctx.check(st, KEY_TYPE, out.data_ptr(), out.numel())
+        edge = torch.stack([out[0], out[-1]]).to(torch.int64) & 0xFFFFFFFF if out.numel() else torch.zeros(2, dtype=torch.int64, device="cuda")
+        edges = [torch.empty_like(edge) for _ in range(world)]
+        dist.all_gather(edges, edge)
+        fp = torch.tensor([before["sum"] & ((1 << 62) - 1), before["hash_xor"] & ((1 << 62) - 1), after["sum"] & ((1 << 62) - 1),
+                           after["hash_xor"] & ((1 << 62) - 1), after["unordered"], out.numel()], dtype=torch.int64, device="cuda")
+        fps = [torch.empty_like(fp) for _ in range(world)]
+        dist.all_gather(fps, fp)
+        fps = torch.stack(fps).cpu().numpy().astype(np.uint64)
+        ok = int(fps[:, 4].sum()) == 0 and int(fps[:, 5].sum()) == total
+        mask = np.uint64((1 << 62) - 1)
+        ok = ok and (np.bitwise_xor.reduce(fps[:, 1]) == np.bitwise_xor.reduce(fps[:, 3]))
+        ok = ok and ((fps[:, 0].sum() & mask) == (fps[:, 2].sum() & mask))
+        e = torch.stack(edges).cpu().numpy()
+        ok = ok and all(e[r, 1] <= e[r + 1, 0] for r in range(world - 1))
+        ok = ok and all(int(fps[r, 5]) == ((r + 1) * total) // world - (r * total) // world for r in range(world))
+        return bool(ok)
+
+    # ---- one instrumented step: device time of every stage (CUDA events; the headline above runs without them) ----
+    ops.stage_events = []
+    step()
+    torch.cuda.synchronize()
+    stages = {}
+    for name, a, b in ops.stage_events:
+        stages[name] = stages.get(name, 0.0) + a.elapsed_time(b)
+    ops.stage_events = None
+    st_t = torch.tensor([stages.get(k, 0.0) for k in ("local_sort", "splitters", "merge_level_1", "merge_levels_local", "final_sort", "closing")],
+                        dtype=torch.float64, device="cuda")
+    dist.all_reduce(st_t, op=dist.ReduceOp.MAX)
+    stage_ms = dict(zip(("local_sort", "splitters", "merge_level_1", "merge_levels_local", "final_sort", "closing"), [round(float(x), 3) for x in st_t.tolist()]))
+
+    # ---- the other four datasets at this size (range / inverted arrive already range-partitioned) ------------------
+    per_dataset = {args.dataset: round(total / ms_max / 1e6, 2)}
+    for kind in ("uniform", "random", "range", "inverted", "zeros"):
+        if kind == args.dataset:
+            continue
+        ctx.fill_dataset(st, KEY_TYPE, kind, shard.data_ptr(), n_local, seed=0x5EED, global_offset=rank * n_local, total_n=total)
+        b4 = ctx.check(st, KEY_TYPE, shard.data_ptr(), n_local)
+        o = step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            o = step()
+        e1.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([e0.elapsed_time(e1) / 3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        if not verify(o, b4):
+            raise RuntimeError(f"bench: distributed output of dataset {kind} failed verification")
+        per_dataset[kind] = round(total / float(tt.item()) / 1e6, 2)
+    ctx.fill_dataset(st, KEY_TYPE, args.dataset, shard.data_ptr(), n_local, seed=0x5EED, global_offset=rank * n_local, total_n=total)
 
     # ---- end to end: shard in pinned host memory -> H2D -> distributed sort -> D2H of this rank's result ----
     def host_mem_available():
@@ -413,46 +563,49 @@ def bench_distributed(args):
     torch.cuda.synchronize()
 
     # global verification: locally sorted, boundaries ordered across ranks, multiset preserved, exact balance
-    after = ctx.check(st, KEY_TYPE, out.data_ptr(), out.numel())
-    edge = torch.stack([out[0], out[-1]]).to(torch.int64) & 0xFFFFFFFF if out.numel() else torch.zeros(2, dtype=torch.int64, device="cuda")
-    edges = [torch.empty_like(edge) for _ in range(world)]
-    dist.all_gather(edges, edge)
-    fp = torch.tensor([before["sum"] & ((1 << 62) - 1), before["hash_xor"] & ((1 << 62) - 1), after["sum"] & ((1 << 62) - 1),
-                       after["hash_xor"] & ((1 << 62) - 1), after["unordered"], out.numel()], dtype=torch.int64, device="cuda")
-    fps = [torch.empty_like(fp) for _ in range(world)]
-    dist.all_gather(fps, fp)
+    ok = verify(out, before)
     if rank == 0:
-        fps = torch.stack(fps).cpu().numpy().astype(np.uint64)
-        ok = int(fps[:, 4].sum()) == 0 and int(fps[:, 5].sum()) == total
-        mask = np.uint64((1 << 62) - 1)
-        ok = ok and (np.bitwise_xor.reduce(fps[:, 1]) == np.bitwise_xor.reduce(fps[:, 3]))
-        ok = ok and ((fps[:, 0].sum() & mask) == (fps[:, 2].sum() & mask))
-        e = torch.stack(edges).cpu().numpy()
-        ok = ok and all(e[r, 1] <= e[r + 1, 0] for r in range(world - 1))
-        ok = ok and all(int(fps[r, 5]) == ((r + 1) * total) // world - (r * total) // world for r in range(world))
         if not ok:
             raise RuntimeError("bench: distributed output failed verification")
         peak, peak_src = measured_hbm_peak()
-        # per GPU: two local sorts (36 B/key each) over HBM, 4*(P-1)/P B/key out and in over NVLink
+        levels = max(1, (world - 1).bit_length())
+        merge_path = exchange == "p2p" and args.final == "merge" and (world & (world - 1)) == 0
+        # algorithmic HBM bytes per key and GPU: the local sort (36) + the final step -- a merge tree reads and writes
+        # every key once per level (8 B/key/level; level 1 reads over NVLink, writes locally), a final sort is 36 more
+        # (the fused pull kernel replaces the histogram read by the NVLink read)
+        sort_bpk = KEY_BYTES + PASSES * 2 * KEY_BYTES
+        hbm_bpk = sort_bpk + (2 * KEY_BYTES * levels if merge_path else sort_bpk)
         nvlink_bytes = KEY_BYTES * n_local * (world - 1) / world
+        lvl1 = stage_ms.get("merge_level_1") or stage_ms.get("final_sort") or None
         line = {
-            "metric": METRIC, "value": total / ms_max / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC_DIST, "value": total / ms_max / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(world, args.dataset), "keys_total": total, "keys_per_gpu": n_local,
                        "exchange": (("pairwise merge tree reading the peers' sorted runs over NVLink (CUDA IPC)" if args.final == "merge"
                                      else "fused peer-memory pull + histogram kernel (CUDA IPC over NVLink) + final onesweep passes")
                                     if exchange == "p2p" else "NCCL all_to_all_single + final local sort"),
-                       "l2": "shards are GiBs, far larger than L2"},
+                       "l2": "shards are GiBs, far larger than L2",
+                       "datasets_gkeys_s": per_dataset,
+                       "exact_parity": f"{parity_cases} reduced-size cases (4 key types x 5 datasets, 2^22 keys) equal to numpy on this box "
+                                       f"before the timed loop; full size: sortedness + cross-rank order + multiset fingerprint + exact balance"},
             "clocks": clocks,
             "e2e": e2e, "gpu_launches": launches * world,
-            "roofline": {"bound": "hbm", "kernel": "whole step per GPU (2 local sorts + exchange)",
-                         "achieved": 2 * (KEY_BYTES + PASSES * 2 * KEY_BYTES) * n_local / (ms_max * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": "whole step per GPU (local sort + " + (f"{levels}-level merge tree)" if merge_path else "final local sort)"),
+                         "algorithmic_bytes_per_key": hbm_bpk,
+                         "achieved": hbm_bpk * n_local / (ms_max * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s", "peak_source": peak_src,
-                         "frac": 2 * (KEY_BYTES + PASSES * 2 * KEY_BYTES) * n_local / (ms_max * 1e-3) / 1e9 / peak,
+                         "frac": hbm_bpk * n_local / (ms_max * 1e-3) / 1e9 / peak,
                          "traffic": None,
-                         "nvlink": {"bytes_out_per_gpu": nvlink_bytes, "peak_gbs_per_direction": 770.0,
-                                    "min_exchange_ms": nvlink_bytes / 770e9 * 1e3}},
+                         "stage_ms_max_over_ranks": stage_ms,
+                         "limits": {"local_sort": "onesweep passes: shared-memory (LSU) bound, see the N=1 line",
+                                    "merge_level_1": "NVLink peer reads", "merge_levels_local": "HBM / LSU (merge-path tile kernel)",
+                                    "splitters": "latency of the refinement rounds (small collectives)"},
+                         "nvlink": {"bytes_in_per_gpu": nvlink_bytes, "peak_gbs": NVLINK_PEER_READ_GBS,
+                                    "peak_source": "measured both-ways peer-read rate of one GPU (tools/peerbw.cu)",
+                                    "exchange_ms": lvl1, "achieved_gbs": (nvlink_bytes / (lvl1 * 1e-3) / 1e9) if lvl1 else None,
+                                    "frac": (nvlink_bytes / (lvl1 * 1e-3) / 1e9 / NVLINK_PEER_READ_GBS) if lvl1 else None,
+                                    "min_exchange_ms": nvlink_bytes / (NVLINK_PEER_READ_GBS * 1e9) * 1e3}},
         }
         print(json.dumps(line), flush=True)
     dist.barrier()
@@ -470,6 +623,7 @@ def main():
     ap.add_argument("--log2n", type=int, default=LOG2_SINGLE, help="single-GPU keys (default 28 = the contract workload)")
     ap.add_argument("--log2n-total", type=int, default=LOG2_DIST_TOTAL, help="multi-GPU total keys (default 33)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (developer runs)")
+    ap.add_argument("--no-other", action="store_true", help="skip the other key types / payload configurations (developer runs)")
     ap.add_argument("--final", default="merge", choices=["merge", "sort"],
                     help="multi-GPU final local step with --exchange p2p: merge tree of the P received sorted runs (default) or a "
                          "full local onesweep sort fed by the fused pull + histogram kernel")

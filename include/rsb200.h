@@ -59,12 +59,25 @@ typedef enum rs_status {
     RS_LOADING_SOURCE_FAILED = 11
 } rs_status;
 
-/* Key types the reference instantiates (src/RadixSortGPU.cpp:598-601). */
+/* Key types.  0..3 are the ones the reference instantiates (src/RadixSortGPU.cpp:598-601); 4 and 5 are the other two
+ * rows of its type table (Common/CLTypeInformation.h:12-22: int16_t / uint16_t), sorted in two passes; 6..9 are
+ * floating-point keys (additive: the reference excludes floats, doc/doc.tex:64).  Floats are ordered by value through
+ * an order-preserving view of their bit patterns applied inside the digit extraction -- keys are stored and moved
+ * unmodified, no extra pass: -inf < ... < -0.0 < +0.0 < ... < +inf < every NaN (NaNs of either sign and any payload
+ * sort last, stable among themselves, as numpy and torch place them).
+ * Integer-only entries (rs_merge_runs_device, rs_lower_bound_device, rs_sorter_sort_segments_device and the multi-GPU
+ * path) reject types >= RS_KEY_F32 and 16-bit keys where stated. */
 typedef enum rs_key_type {
     RS_KEY_U32 = 0,
     RS_KEY_I32 = 1,
     RS_KEY_U64 = 2,
-    RS_KEY_I64 = 3
+    RS_KEY_I64 = 3,
+    RS_KEY_U16 = 4,
+    RS_KEY_I16 = 5,
+    RS_KEY_F32 = 6,
+    RS_KEY_F64 = 7,
+    RS_KEY_F16 = 8,  /* IEEE binary16 */
+    RS_KEY_BF16 = 9  /* bfloat16 */
 } rs_key_type;
 
 /* Dataset generators of the reference (src/Dataset.h:84-137). */

@@ -15,8 +15,10 @@ HEADER = os.path.join(ROOT, "include", "rsb200.h")
 # RSB200_LIB: developer override to A/B a differently tuned build of the same library (tools/build_variants.sh)
 _LIB_PATH = os.environ.get("RSB200_LIB") or os.path.join(HERE, "librsb200.so")
 
-KEY_TYPES = {"u32": 0, "i32": 1, "u64": 2, "i64": 3}
-_NP = {"u32": np.uint32, "i32": np.int32, "u64": np.uint64, "i64": np.int64}
+KEY_TYPES = {"u32": 0, "i32": 1, "u64": 2, "i64": 3, "u16": 4, "i16": 5, "f32": 6, "f64": 7, "f16": 8, "bf16": 9}
+# host-side storage dtype of a key type (bf16 has no numpy dtype: its bit patterns travel as uint16)
+_NP = {"u32": np.uint32, "i32": np.int32, "u64": np.uint64, "i64": np.int64, "u16": np.uint16, "i16": np.int16,
+       "f32": np.float32, "f64": np.float64, "f16": np.float16, "bf16": np.uint16}
 DATASET_KINDS = {"zeros": 0, "range": 1, "inverted": 2, "uniform": 3, "random": 4}
 RS_WITH_PERMUTATION, RS_NO_TMA, RS_NO_PROFILE, RS_NO_KEY_BUFFERS, RS_NO_PASS_SKIP, RS_NO_ATOMIC_RANK, RS_NO_SMALL_PATH = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40
 

@@ -18,10 +18,13 @@ struct TypeNameString {};
         inline static constexpr bool             sortable     = HAS_KEY; \
         inline static constexpr rs_key_type      key_type     = KEY;     \
     };
-RS_TYPE_ROW(int16_t, "short", false, RS_KEY_I32)            // named by the reference, not instantiated by its sorter
-RS_TYPE_ROW(uint16_t, "unsigned short", false, RS_KEY_U32)  // (src/RadixSortGPU.cpp:598-601)
+RS_TYPE_ROW(int16_t, "short", true, RS_KEY_I16)            // named by the reference's table, not instantiated by its sorter
+RS_TYPE_ROW(uint16_t, "unsigned short", true, RS_KEY_U16)  // (src/RadixSortGPU.cpp:598-601); here: two 8-bit passes
 RS_TYPE_ROW(int32_t, "int", true, RS_KEY_I32)
 RS_TYPE_ROW(uint32_t, "unsigned int", true, RS_KEY_U32)
 RS_TYPE_ROW(int64_t, "long", true, RS_KEY_I64)
 RS_TYPE_ROW(uint64_t, "unsigned long", true, RS_KEY_U64)
+// additive (the reference excludes floating point, doc/doc.tex:64): ordered by value, NaNs last (rsb200.h rs_key_type)
+RS_TYPE_ROW(float, "float", true, RS_KEY_F32)
+RS_TYPE_ROW(double, "double", true, RS_KEY_F64)
 #undef RS_TYPE_ROW

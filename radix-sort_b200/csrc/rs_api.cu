@@ -7,6 +7,7 @@
 // kernel, the scan kernel and one onesweep kernel per 8-bit digit are enqueued back to back.
 #include "../../include/rsb200.h"
 #include "rs_kernels.cuh"
+#include "rs_sweep.cuh"
 #include "rs_merge.cuh"
 
 #include <algorithm>
@@ -14,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -48,11 +50,51 @@ static int fail(int status, const char* what, cudaError_t e = cudaSuccess) {
         if (_e != cudaSuccess) return fail((status), #expr, _e); \
     } while (0)
 
+// Key-type table (what TypeNameString<T> + the generated `#define DataType` preamble are in the reference,
+// Common/CLTypeInformation.h:8-46, src/RadixSortGPU.cpp:431-442).
+struct KeyInfo {
+    size_t             bytes;
+    bool               is_signed;  // two's-complement integers: the sign bit is flipped in the digit that holds it
+    unsigned long long finf;       // floating point: bit pattern of +infinity (see float_order_bits), else 0
+};
+static bool key_info(int type, KeyInfo* out) {
+    switch (type) {
+        case RS_KEY_U32:  *out = {4, false, 0}; return true;
+        case RS_KEY_I32:  *out = {4, true, 0}; return true;
+        case RS_KEY_U64:  *out = {8, false, 0}; return true;
+        case RS_KEY_I64:  *out = {8, true, 0}; return true;
+        case RS_KEY_U16:  *out = {2, false, 0}; return true;
+        case RS_KEY_I16:  *out = {2, true, 0}; return true;
+        case RS_KEY_F32:  *out = {4, false, 0x7f800000ull}; return true;
+        case RS_KEY_F64:  *out = {8, false, 0x7ff0000000000000ull}; return true;
+        case RS_KEY_F16:  *out = {2, false, 0x7c00ull}; return true;
+        case RS_KEY_BF16: *out = {2, false, 0x7f80ull}; return true;
+    }
+    return false;
+}
+
+// Every entry runs on its context's device and puts the calling thread's current device back afterwards (a torch
+// caller may be working on another GPU).
+struct DeviceGuard {
+    int  prev = -1;
+    bool switched = false;
+    cudaError_t status = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) { status = cudaSetDevice(device); switched = status == cudaSuccess; }
+    }
+    ~DeviceGuard() { if (switched && prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 struct rs_context_s {
     int device;
     int sm_count;
     int max_smem_optin;
     int atomic_rank_ok;  // the device passed rs_atomic_order_selftest_kernel (same-word shared atomics in lane order)
+    unsigned long long* d_result;  // 8 words for the blocking *_device checks (no cudaMalloc per call)
+    std::mutex          result_mutex;
 };
 struct rs_stream_s {
     rs_context   ctx;
@@ -71,6 +113,7 @@ struct rs_sorter_s {
     uint64_t    max_keys;
     size_t      key_bytes;
     bool        is_signed;
+    unsigned long long finf;  // floating-point keys: +infinity bit pattern (0 for integers)
     bool        has_vals;
     bool        atomic_rank;  // ranking mode of the onesweep kernel (see rs_kernels.cuh)
     // device memory
@@ -151,11 +194,14 @@ template <> struct TileCfg<uint32_t, true,  true>  { static constexpr int THREAD
 template <> struct TileCfg<uint64_t, false, true>  { static constexpr int THREADS = RS_U64A_THREADS, KPT = RS_U64A_KPT, MINB = RS_U64A_MINB; };
 template <> struct TileCfg<uint64_t, true,  true>  { static constexpr int THREADS = RS_U64VA_THREADS, KPT = RS_U64VA_KPT, MINB = RS_U64VA_MINB; };
 
+// 16-bit keys (two passes): same shapes as 32-bit keys -- a key still takes one register
+template <bool V, bool A> struct TileCfg<uint16_t, V, A> : TileCfg<uint32_t, V, A> {};
+
 template <typename KeyT, bool HAS_VALS, bool ATOMIC>
 static constexpr int tile_of() { return TileCfg<KeyT, HAS_VALS, ATOMIC>::THREADS * TileCfg<KeyT, HAS_VALS, ATOMIC>::KPT; }
 
 static int tile_keys(size_t key_bytes, bool has_vals, bool atomic) {
-    if (key_bytes == 4) {
+    if (key_bytes <= 4) {
         if (atomic) return has_vals ? tile_of<uint32_t, true, true>() : tile_of<uint32_t, false, true>();
         return has_vals ? tile_of<uint32_t, true, false>() : tile_of<uint32_t, false, false>();
     }
@@ -198,23 +244,27 @@ static Plan make_plan(uint64_t n, size_t key_bytes, bool has_vals, bool atomic, 
     return p;
 }
 
-template <typename KeyT, int NPASS>
-static cudaError_t launch_hist_n(int grid, cudaStream_t st, const KeyT* keys, uint64_t n, const Plan&,
-                                 unsigned long long* hist, const PassTable& pt) {
-    auto kern = rs_histogram_kernel<KeyT, NPASS>;
-    static thread_local uint64_t configured = 0;
-    if (const uint64_t bit = current_device_bit(); !(configured & bit)) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(HistCfg<NPASS>::bytes));
-        if (e != cudaSuccess) return e;
-        configured |= bit;
+template <typename KeyT, int NPASS, bool FK>
+static cudaError_t launch_hist_n(int grid, cudaStream_t st, const KeyT* keys, uint64_t n, unsigned long long* hist,
+                                 const PassTable& pt) {
+    if constexpr (NPASS > static_cast<int>(sizeof(KeyT))) {
+        return cudaErrorInvalidValue;  // more 8-bit digits than the key has
+    } else {
+        auto kern = rs_histogram_kernel<KeyT, NPASS, FK>;
+        static thread_local uint64_t configured = 0;
+        if (const uint64_t bit = current_device_bit(); !(configured & bit)) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(HistCfg<NPASS>::bytes));
+            if (e != cudaSuccess) return e;
+            configured |= bit;
+        }
+        kern<<<grid, HIST_THREADS, HistCfg<NPASS>::bytes, st>>>(keys, n, hist, pt);
+        return cudaGetLastError();
     }
-    kern<<<grid, HIST_THREADS, HistCfg<NPASS>::bytes, st>>>(keys, n, hist, pt);
-    return cudaGetLastError();
 }
-template <typename KeyT>
-static cudaError_t launch_hist(int sm_count, cudaStream_t st, const KeyT* keys, uint64_t n, const Plan& pl,
-                               unsigned long long* hist, const PassTable& pt) {
+template <typename KeyT, bool FK>
+static cudaError_t launch_hist(int sm_count, cudaStream_t st, const KeyT* keys, uint64_t n, unsigned long long* hist,
+                               const PassTable& pt) {
     const uint64_t vec_per_block = static_cast<uint64_t>(HIST_THREADS) * HIST_VECS * (16 / sizeof(KeyT));
     uint64_t want = (n + vec_per_block - 1) / vec_per_block;
     // one block per SM (the per-lane tables take most of the shared memory); 32-bit counters: < 2^31 keys per block
@@ -222,14 +272,14 @@ static cudaError_t launch_hist(int sm_count, cudaStream_t st, const KeyT* keys, 
     int grid = static_cast<int>(std::max<uint64_t>(
         min_grid, std::min<uint64_t>(std::max<uint64_t>(want, 1), static_cast<uint64_t>(sm_count))));
     switch (pt.num_passes) {
-        case 1: return launch_hist_n<KeyT, 1>(grid, st, keys, n, pl, hist, pt);
-        case 2: return launch_hist_n<KeyT, 2>(grid, st, keys, n, pl, hist, pt);
-        case 3: return launch_hist_n<KeyT, 3>(grid, st, keys, n, pl, hist, pt);
-        case 4: return launch_hist_n<KeyT, 4>(grid, st, keys, n, pl, hist, pt);
-        case 5: return launch_hist_n<KeyT, 5>(grid, st, keys, n, pl, hist, pt);
-        case 6: return launch_hist_n<KeyT, 6>(grid, st, keys, n, pl, hist, pt);
-        case 7: return launch_hist_n<KeyT, 7>(grid, st, keys, n, pl, hist, pt);
-        case 8: return launch_hist_n<KeyT, 8>(grid, st, keys, n, pl, hist, pt);
+        case 1: return launch_hist_n<KeyT, 1, FK>(grid, st, keys, n, hist, pt);
+        case 2: return launch_hist_n<KeyT, 2, FK>(grid, st, keys, n, hist, pt);
+        case 3: return launch_hist_n<KeyT, 3, FK>(grid, st, keys, n, hist, pt);
+        case 4: return launch_hist_n<KeyT, 4, FK>(grid, st, keys, n, hist, pt);
+        case 5: return launch_hist_n<KeyT, 5, FK>(grid, st, keys, n, hist, pt);
+        case 6: return launch_hist_n<KeyT, 6, FK>(grid, st, keys, n, hist, pt);
+        case 7: return launch_hist_n<KeyT, 7, FK>(grid, st, keys, n, hist, pt);
+        case 8: return launch_hist_n<KeyT, 8, FK>(grid, st, keys, n, hist, pt);
     }
     return cudaErrorInvalidValue;
 }
@@ -237,16 +287,20 @@ static cudaError_t launch_hist(int sm_count, cudaStream_t st, const KeyT* keys, 
 template <typename KeyT, int NPASS>
 static cudaError_t launch_gather_hist_n(int grid, cudaStream_t st, const SegmentTable<KeyT>& seg, KeyT* gathered,
                                         unsigned long long* hist, const PassTable& pt) {
-    auto kern = rs_gather_histogram_kernel<KeyT, NPASS>;
-    static thread_local uint64_t configured = 0;
-    if (const uint64_t bit = current_device_bit(); !(configured & bit)) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(HistCfg<NPASS>::bytes));
-        if (e != cudaSuccess) return e;
-        configured |= bit;
+    if constexpr (NPASS > static_cast<int>(sizeof(KeyT))) {
+        return cudaErrorInvalidValue;
+    } else {
+        auto kern = rs_gather_histogram_kernel<KeyT, NPASS>;
+        static thread_local uint64_t configured = 0;
+        if (const uint64_t bit = current_device_bit(); !(configured & bit)) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(HistCfg<NPASS>::bytes));
+            if (e != cudaSuccess) return e;
+            configured |= bit;
+        }
+        kern<<<grid, HIST_THREADS, HistCfg<NPASS>::bytes, st>>>(seg, gathered, hist, pt);
+        return cudaGetLastError();
     }
-    kern<<<grid, HIST_THREADS, HistCfg<NPASS>::bytes, st>>>(seg, gathered, hist, pt);
-    return cudaGetLastError();
 }
 template <typename KeyT>
 static cudaError_t launch_gather_hist(int sm_count, cudaStream_t st, const SegmentTable<KeyT>& seg, KeyT* gathered,
@@ -266,32 +320,65 @@ static cudaError_t launch_gather_hist(int sm_count, cudaStream_t st, const Segme
     return cudaErrorInvalidValue;
 }
 
-template <typename KeyT, bool HAS_VALS, bool ATOMIC>
-static cudaError_t launch_pass_mode(rs_context ctx, cudaStream_t st, const OnesweepArgs<KeyT>& args) {
-    using C = TileCfg<KeyT, HAS_VALS, ATOMIC>;
-    using L = OnesweepSmem<KeyT, HAS_VALS, C::THREADS, C::KPT, ATOMIC>;
-    auto kern = rs_onesweep_kernel<KeyT, HAS_VALS, C::THREADS, C::KPT, C::MINB, ATOMIC>;
-    static thread_local int cached_device = -1;
-    static thread_local int blocks_per_sm = 0;
-    if (cached_device != ctx->device) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::total));
+// Per-kernel launch state: dynamic shared memory attribute and resident CTAs per SM, per device (a process may hold
+// contexts on several GPUs and alternate between them).
+struct PassLaunchState {
+    int blocks_per_sm[64] = {};
+};
+template <typename Kern>
+static cudaError_t configure_pass(Kern kern, int device, int threads, size_t smem, PassLaunchState& st, int* blocks_per_sm) {
+    int& b = st.blocks_per_sm[device & 63];
+    if (!b) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, C::THREADS, L::total);
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
         if (e != cudaSuccess) return e;
-        if (blocks_per_sm < 1) return cudaErrorLaunchOutOfResources;
-        cached_device = ctx->device;
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+        b = occ;
     }
-    const uint64_t resident = static_cast<uint64_t>(blocks_per_sm) * ctx->sm_count;
-    const int grid = static_cast<int>(std::min<uint64_t>(args.num_tiles, resident));
-    kern<<<grid, C::THREADS, L::total, st>>>(args);
-    return cudaGetLastError();
-}
-template <typename KeyT, bool HAS_VALS>
-static cudaError_t launch_pass(rs_context ctx, cudaStream_t st, const OnesweepArgs<KeyT>& args, bool atomic) {
-    return atomic ? launch_pass_mode<KeyT, HAS_VALS, true>(ctx, st, args) : launch_pass_mode<KeyT, HAS_VALS, false>(ctx, st, args);
+    *blocks_per_sm = b;
+    return cudaSuccess;
 }
 
-static PassTable make_pass_table(size_t key_bytes, bool is_signed, int begin_bit, int end_bit) {
+template <typename KeyT, bool HAS_VALS, bool ATOMIC, bool FK>
+static cudaError_t launch_pass_mode(rs_context ctx, cudaStream_t st, const OnesweepArgs<KeyT>& args) {
+    using C = TileCfg<KeyT, HAS_VALS, ATOMIC>;
+    int blocks_per_sm = 0;
+    if constexpr (ATOMIC) {
+        // A/B switch: the first-generation kernel in its atomic mode (same tile shape, same scratch layout); integer keys
+        static const bool sweep_v1 = std::getenv("RSB200_SWEEP_V1") != nullptr;
+        bool use_v1 = false;
+        if constexpr (!FK && sizeof(KeyT) >= 4) use_v1 = sweep_v1;
+        if (!use_v1) {
+            using L = SweepSmem<KeyT, HAS_VALS, C::THREADS, C::KPT>;
+            auto kern = rs_sweep_kernel<KeyT, HAS_VALS, C::THREADS, C::KPT, C::MINB, FK>;
+            static thread_local PassLaunchState state;
+            cudaError_t e = configure_pass(kern, ctx->device, C::THREADS, L::total, state, &blocks_per_sm);
+            if (e != cudaSuccess) return e;
+            const uint64_t resident = static_cast<uint64_t>(blocks_per_sm) * ctx->sm_count;
+            kern<<<static_cast<int>(std::min<uint64_t>(args.num_tiles, resident)), C::THREADS, L::total, st>>>(args);
+            return cudaGetLastError();
+        }
+    }
+    if constexpr (!ATOMIC || (!FK && sizeof(KeyT) >= 4)) {
+        using L = OnesweepSmem<KeyT, HAS_VALS, C::THREADS, C::KPT, ATOMIC>;
+        auto kern = rs_onesweep_kernel<KeyT, HAS_VALS, C::THREADS, C::KPT, C::MINB, ATOMIC, FK>;
+        static thread_local PassLaunchState state;
+        cudaError_t e = configure_pass(kern, ctx->device, C::THREADS, L::total, state, &blocks_per_sm);
+        if (e != cudaSuccess) return e;
+        const uint64_t resident = static_cast<uint64_t>(blocks_per_sm) * ctx->sm_count;
+        kern<<<static_cast<int>(std::min<uint64_t>(args.num_tiles, resident)), C::THREADS, L::total, st>>>(args);
+        return cudaGetLastError();
+    }
+    return cudaErrorInvalidValue;
+}
+template <typename KeyT, bool HAS_VALS, bool FK>
+static cudaError_t launch_pass(rs_context ctx, cudaStream_t st, const OnesweepArgs<KeyT>& args, bool atomic) {
+    return atomic ? launch_pass_mode<KeyT, HAS_VALS, true, FK>(ctx, st, args) : launch_pass_mode<KeyT, HAS_VALS, false, FK>(ctx, st, args);
+}
+
+static PassTable make_pass_table(size_t key_bytes, bool is_signed, unsigned long long finf, int begin_bit, int end_bit) {
     PassTable pt{};
     const int key_bits = static_cast<int>(key_bytes) * 8;
     int p = 0;
@@ -300,18 +387,19 @@ static PassTable make_pass_table(size_t key_bytes, bool is_signed, int begin_bit
         pt.d[p].shift  = b;
         pt.d[p].mask   = (1u << bits) - 1u;
         pt.d[p].flip   = 0;
+        pt.d[p].finf   = finf;
         if (is_signed && key_bits - 1 >= b && key_bits - 1 < b + bits) pt.d[p].flip = 1u << (key_bits - 1 - b);
     }
     pt.num_passes = p;
     return pt;
 }
 
-template <typename KeyT>
-static int sort_typed(rs_sorter s, cudaStream_t st, const KeyT* in, KeyT* buf0, KeyT* buf1, const uint32_t* vin,
+template <typename KeyT, bool FK>
+static int sort_typed_fk(rs_sorter s, cudaStream_t st, const KeyT* in, KeyT* buf0, KeyT* buf1, const uint32_t* vin,
                       uint32_t* vbuf0, uint32_t* vbuf1, uint64_t n, int begin_bit, int end_bit, bool profile,
-                      int* result_index, const SegmentTable<KeyT>* segments = nullptr) {
+                      int* result_index, const SegmentTable<KeyT>* segments) {
     const bool has_vals = vin != nullptr;
-    const PassTable pt = make_pass_table(sizeof(KeyT), s->is_signed, begin_bit, end_bit);
+    const PassTable pt = make_pass_table(sizeof(KeyT), s->is_signed, s->finf, begin_bit, end_bit);
     if (pt.num_passes < 1) return fail(RS_CALCULATION_FAILED, "empty bit range");
     const Plan pl = make_plan(n, sizeof(KeyT), has_vals, s->atomic_rank, pt.num_passes);
     if (pl.total > s->scratch_bytes) return fail(RS_CALCULATION_FAILED, "n exceeds the sorter's max_keys (scratch too small)");
@@ -332,13 +420,13 @@ static int sort_typed(rs_sorter s, cudaStream_t st, const KeyT* in, KeyT* buf0, 
         const int allow = (s->flags & RS_NO_PASS_SKIP) ? 0 : 1;
         cudaError_t e;
         if (has_vals) {
-            auto kern = rs_small_sort_kernel<KeyT, true>;
+            auto kern = rs_small_sort_kernel<KeyT, true, FK>;
             static thread_local uint64_t cfg = 0;
             if (const uint64_t bit = current_device_bit(); !(cfg & bit)) { RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SmallSmem<KeyT, true>::total)), RS_CALCULATION_FAILED); cfg |= bit; }
             kern<<<1, SMALL_THREADS, SmallSmem<KeyT, true>::total, st>>>(in, kout, vin, vout, static_cast<uint32_t>(n), pt, hist_s, plan_s, allow);
             e = cudaGetLastError();
         } else {
-            auto kern = rs_small_sort_kernel<KeyT, false>;
+            auto kern = rs_small_sort_kernel<KeyT, false, FK>;
             static thread_local uint64_t cfg = 0;
             if (const uint64_t bit = current_device_bit(); !(cfg & bit)) { RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SmallSmem<KeyT, false>::total)), RS_CALCULATION_FAILED); cfg |= bit; }
             kern<<<1, SMALL_THREADS, SmallSmem<KeyT, false>::total, st>>>(in, kout, nullptr, nullptr, static_cast<uint32_t>(n), pt, hist_s, plan_s, allow);
@@ -374,10 +462,14 @@ static int sort_typed(rs_sorter s, cudaStream_t st, const KeyT* in, KeyT* buf0, 
     auto* base   = reinterpret_cast<unsigned long long*>(s->scratch + pl.off_base);
 
     RS_CUDA(cudaMemsetAsync(s->scratch, 0, pl.zero_bytes, st), RS_CALCULATION_FAILED);
-    if (segments)  // multi-GPU: pull the peer segments into `in` and count them in the same kernel
-        RS_CUDA(launch_gather_hist<KeyT>(s->ctx->sm_count, st, *segments, const_cast<KeyT*>(in), n, hist, pt), RS_CALCULATION_FAILED);
-    else
-        RS_CUDA(launch_hist<KeyT>(s->ctx->sm_count, st, in, n, pl, hist, pt), RS_CALCULATION_FAILED);
+    if (segments) {  // multi-GPU: pull the peer segments into `in` and count them in the same kernel (integer keys of 4 / 8 bytes)
+        if constexpr (!FK && sizeof(KeyT) >= 4)
+            RS_CUDA(launch_gather_hist<KeyT>(s->ctx->sm_count, st, *segments, const_cast<KeyT*>(in), n, hist, pt), RS_CALCULATION_FAILED);
+        else
+            return fail(RS_CALCULATION_FAILED, "the fused gather + sort entry serves 4- and 8-byte integer keys");
+    } else {
+        RS_CUDA((launch_hist<KeyT, FK>(s->ctx->sm_count, st, in, n, hist, pt)), RS_CALCULATION_FAILED);
+    }
     s->launches++;
     if (profile) RS_CUDA(cudaEventRecord(q.e[1], st), RS_CALCULATION_FAILED);
     auto* plan = reinterpret_cast<SortPlanDev*>(s->scratch + pl.off_plan);
@@ -409,8 +501,8 @@ static int sort_typed(rs_sorter s, cudaStream_t st, const KeyT* in, KeyT* buf0, 
         a.num_chunks      = static_cast<uint32_t>(pl.num_chunks);
         a.digit           = pt.d[p];
         a.use_tma         = ((s->flags & RS_NO_TMA) == 0) && all_aligned;
-        cudaError_t e = has_vals ? launch_pass<KeyT, true>(s->ctx, st, a, s->atomic_rank)
-                                 : launch_pass<KeyT, false>(s->ctx, st, a, s->atomic_rank);
+        cudaError_t e = has_vals ? launch_pass<KeyT, true, FK>(s->ctx, st, a, s->atomic_rank)
+                                 : launch_pass<KeyT, false, FK>(s->ctx, st, a, s->atomic_rank);
         if (e != cudaSuccess) return fail(RS_CALCULATION_FAILED, "onesweep launch", e);
         s->launches++;
     }
@@ -424,6 +516,14 @@ static int sort_typed(rs_sorter s, cudaStream_t st, const KeyT* in, KeyT* buf0, 
     s->last_plan_offset = pl.off_plan;
     if (result_index) *result_index = (pt.num_passes - 1) & 1;
     return RS_OK;
+}
+
+template <typename KeyT>
+static int sort_typed(rs_sorter s, cudaStream_t st, const KeyT* in, KeyT* buf0, KeyT* buf1, const uint32_t* vin,
+                      uint32_t* vbuf0, uint32_t* vbuf1, uint64_t n, int begin_bit, int end_bit, bool profile,
+                      int* result_index, const SegmentTable<KeyT>* segments = nullptr) {
+    return s->finf ? sort_typed_fk<KeyT, true>(s, st, in, buf0, buf1, vin, vbuf0, vbuf1, n, begin_bit, end_bit, profile, result_index, segments)
+                   : sort_typed_fk<KeyT, false>(s, st, in, buf0, buf1, vin, vbuf0, vbuf1, n, begin_bit, end_bit, profile, result_index, segments);
 }
 
 static int resolve_pending(rs_sorter s, bool block) {
@@ -512,15 +612,21 @@ __device__ __forceinline__ unsigned long long warp_xor(unsigned long long v) {
     return v;
 }
 
+// key -> unsigned value in the key type's order: sign bit flipped for signed integers, float_order_bits for floats
 template <typename U>
-__global__ void rs_check_kernel(const U* keys, uint64_t n, U sign, unsigned long long* result) {
+__device__ __forceinline__ U ordered_key(U k, U sign, unsigned long long finf) {
+    return finf ? float_order_bits(k, finf) : static_cast<U>(k ^ sign);
+}
+
+template <typename U>
+__global__ void rs_check_kernel(const U* keys, uint64_t n, U sign, unsigned long long finf, unsigned long long* result) {
     unsigned long long bad = 0, sum = 0, hsum = 0, hxor = 0;
     for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
         const U k = keys[i];
         if (i + 1 < n) {
             const U nx = keys[i + 1];
-            if (static_cast<U>(nx ^ sign) < static_cast<U>(k ^ sign)) bad++;
+            if (ordered_key(nx, sign, finf) < ordered_key(k, sign, finf)) bad++;
         }
         const unsigned long long h = mix64(static_cast<uint64_t>(k) + 0x9E3779B97F4A7C15ull);
         sum += static_cast<uint64_t>(k);
@@ -694,6 +800,14 @@ static int merge_runs_typed(rs_context ctx, cudaStream_t st, bool is_signed, int
     return RS_OK;
 }
 
+// typed dispatch over the key width: f(U{}) with U = uint16_t / uint32_t / uint64_t
+template <typename F>
+static void for_key_width(size_t bytes, F&& f) {
+    if (bytes == 2) f(uint16_t{});
+    else if (bytes == 4) f(uint32_t{});
+    else f(uint64_t{});
+}
+
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
@@ -730,14 +844,19 @@ int rs_context_create(int device, rs_context* out) {
     int count = 0;
     RS_CUDA(cudaGetDeviceCount(&count), RS_INITIALIZATION_FAILED);
     if (device < 0 || device >= count) return fail(RS_INITIALIZATION_FAILED, "no such CUDA device");
-    RS_CUDA(cudaSetDevice(device), RS_INITIALIZATION_FAILED);
+    DeviceGuard guard(device); if (guard.status != cudaSuccess) return fail(RS_INITIALIZATION_FAILED, "cudaSetDevice", guard.status);
     int major = 0, sms = 0, smem = 0;
     RS_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device), RS_INITIALIZATION_FAILED);
     RS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device), RS_INITIALIZATION_FAILED);
     RS_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device), RS_INITIALIZATION_FAILED);
     if (major != 10) return fail(RS_INITIALIZATION_FAILED, "librsb200 is built for sm_100a (B200) only");
-    rs_context c = new (std::nothrow) rs_context_s{device, sms, smem, 0};
+    rs_context c = new (std::nothrow) rs_context_s{};
     if (!c) return fail(RS_INITIALIZATION_FAILED, "out of host memory");
+    c->device = device; c->sm_count = sms; c->max_smem_optin = smem;
+    if (cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->d_result), 8 * sizeof(unsigned long long)); e != cudaSuccess) {
+        delete c;
+        return fail(RS_INITIALIZATION_FAILED, "cudaMalloc", e);
+    }
     {   // self-test behind the atomic ranking mode (a few hundred microseconds; see rs_kernels.cuh)
         unsigned long long* d_bad = nullptr;
         unsigned long long  h_bad = 1;
@@ -756,6 +875,9 @@ int rs_context_create(int device, rs_context* out) {
 }
 
 int rs_context_destroy(rs_context ctx) {
+    if (!ctx) return RS_OK;
+    DeviceGuard guard(ctx->device);
+    if (ctx->d_result) cudaFree(ctx->d_result);
     delete ctx;
     return RS_OK;
 }
@@ -774,7 +896,7 @@ int rs_context_sm_count(rs_context ctx, int* n) {
 
 int rs_stream_create(rs_context ctx, rs_stream* out) {
     if (!ctx || !out) return fail(RS_INITIALIZATION_FAILED, "null argument");
-    RS_CUDA(cudaSetDevice(ctx->device), RS_INITIALIZATION_FAILED);
+    DeviceGuard guard(ctx->device); if (guard.status != cudaSuccess) return fail(RS_INITIALIZATION_FAILED, "cudaSetDevice", guard.status);
     cudaStream_t st;
     RS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), RS_INITIALIZATION_FAILED);
     *out = new rs_stream_s{ctx, st, true};
@@ -789,7 +911,7 @@ int rs_stream_wrap(rs_context ctx, void* cuda_stream, rs_stream* out) {
 
 int rs_stream_sync(rs_stream s) {
     if (!s) return fail(RS_CALCULATION_FAILED, "null stream");
-    RS_CUDA(cudaSetDevice(s->ctx->device), RS_CALCULATION_FAILED);
+    DeviceGuard guard(s->ctx->device); if (guard.status != cudaSuccess) return fail(RS_CALCULATION_FAILED, "cudaSetDevice", guard.status);
     RS_CUDA(cudaStreamSynchronize(s->st), RS_CALCULATION_FAILED);
     return RS_OK;
 }
@@ -797,7 +919,7 @@ int rs_stream_sync(rs_stream s) {
 int rs_stream_destroy(rs_stream s) {
     if (!s) return RS_OK;
     if (s->owned) {
-        cudaSetDevice(s->ctx->device);
+        DeviceGuard guard(s->ctx->device);
         cudaStreamDestroy(s->st);
     }
     delete s;
@@ -824,16 +946,18 @@ uint64_t rs_round_up_keys(uint64_t n) {
 int rs_sorter_create(rs_context ctx, rs_key_type type, uint64_t max_keys, uint32_t flags, rs_sorter* out) {
     if (!ctx || !out) return fail(RS_INITIALIZATION_FAILED, "null argument");
     *out = nullptr;
-    if (type < RS_KEY_U32 || type > RS_KEY_I64) return fail(RS_INITIALIZATION_FAILED, "unknown key type");
-    RS_CUDA(cudaSetDevice(ctx->device), RS_INITIALIZATION_FAILED);
+    KeyInfo ki{};
+    if (!key_info(type, &ki)) return fail(RS_INITIALIZATION_FAILED, "unknown key type");
+    DeviceGuard guard(ctx->device); if (guard.status != cudaSuccess) return fail(RS_INITIALIZATION_FAILED, "cudaSetDevice", guard.status);
     rs_sorter s = new (std::nothrow) rs_sorter_s{};
     if (!s) return fail(RS_INITIALIZATION_FAILED, "out of host memory");
     s->ctx       = ctx;
     s->type      = type;
     s->flags     = flags;
     s->max_keys  = max_keys;
-    s->key_bytes = (type == RS_KEY_U32 || type == RS_KEY_I32) ? 4 : 8;
-    s->is_signed = (type == RS_KEY_I32 || type == RS_KEY_I64);
+    s->key_bytes = ki.bytes;
+    s->is_signed = ki.is_signed;
+    s->finf      = ki.finf;
     s->has_vals  = (flags & RS_WITH_PERMUTATION) != 0;
     s->atomic_rank = ctx->atomic_rank_ok && !(flags & RS_NO_ATOMIC_RANK);
     stat_reset(s->rt.time_histo); stat_reset(s->rt.time_scan); stat_reset(s->rt.time_reorder);
@@ -866,7 +990,7 @@ int rs_sorter_create(rs_context ctx, rs_key_type type, uint64_t max_keys, uint32
 
 int rs_sorter_destroy(rs_sorter s) {
     if (!s) return RS_OK;
-    cudaSetDevice(s->ctx->device);
+    DeviceGuard guard(s->ctx->device);
     int rc = RS_OK;
     for (auto& q : s->pending) for (auto& e : q.e) cudaEventDestroy(e);
     for (auto& q : s->free_events) for (auto& e : q.e) cudaEventDestroy(e);
@@ -884,16 +1008,19 @@ int rs_sorter_pad(rs_sorter s, rs_stream st, uint64_t first_key, uint64_t rounde
     if (!s->keys[0]) return fail(RS_CALCULATION_FAILED, "sorter has no key buffers");
     if (rounded > s->max_keys || first_key > rounded) return fail(RS_RESIZE_FAILED, "pad range exceeds max_keys");
     if (first_key == rounded) return RS_OK;
-    RS_CUDA(cudaSetDevice(s->ctx->device), RS_CALCULATION_FAILED);
+    DeviceGuard guard(s->ctx->device); if (guard.status != cudaSuccess) return fail(RS_CALCULATION_FAILED, "cudaSetDevice", guard.status);
     const int g = grid_for(rounded - first_key, 256, s->ctx->sm_count);
     // pattern = numeric_limits<T>::max() - 1 (src/RadixSortGPU.cpp:274-276)
-    if (s->key_bytes == 4) {
-        const uint32_t v = (s->is_signed ? 0x7fffffffu : 0xffffffffu) - 1u;
-        rs_fill_value_kernel<uint32_t><<<g, 256, 0, st->st>>>(static_cast<uint32_t*>(s->keys[0]), first_key, rounded, v);
-    } else {
-        const uint64_t v = (s->is_signed ? 0x7fffffffffffffffull : 0xffffffffffffffffull) - 1ull;
+    // floating point: max() - 1 rounds to max(), i.e. the pattern just below +infinity
+    const int      bits = static_cast<int>(s->key_bytes) * 8;
+    const uint64_t all  = bits == 64 ? ~0ull : ((1ull << bits) - 1ull);
+    const uint64_t v    = s->finf ? s->finf - 1ull : (s->is_signed ? (all >> 1) : all) - 1ull;
+    if (s->key_bytes == 2)
+        rs_fill_value_kernel<uint16_t><<<g, 256, 0, st->st>>>(static_cast<uint16_t*>(s->keys[0]), first_key, rounded, static_cast<uint16_t>(v));
+    else if (s->key_bytes == 4)
+        rs_fill_value_kernel<uint32_t><<<g, 256, 0, st->st>>>(static_cast<uint32_t*>(s->keys[0]), first_key, rounded, static_cast<uint32_t>(v));
+    else
         rs_fill_value_kernel<uint64_t><<<g, 256, 0, st->st>>>(static_cast<uint64_t*>(s->keys[0]), first_key, rounded, v);
-    }
     RS_CUDA(cudaGetLastError(), RS_CALCULATION_FAILED);
     s->launches++;
     return RS_OK;
@@ -904,7 +1031,7 @@ int rs_sorter_upload(rs_sorter s, rs_stream st, const void* h_keys, const uint32
     if (!s->keys[0]) return fail(RS_DATA_UPLOAD_FAILED, "sorter has no key buffers");
     if (n > s->max_keys) return fail(RS_DATA_UPLOAD_FAILED, "n exceeds max_keys");
     if (n && !h_keys) return fail(RS_HOST_BUFFERS_FAILED, "null host key buffer");
-    RS_CUDA(cudaSetDevice(s->ctx->device), RS_DATA_UPLOAD_FAILED);
+    DeviceGuard guard(s->ctx->device); if (guard.status != cudaSuccess) return fail(RS_DATA_UPLOAD_FAILED, "cudaSetDevice", guard.status);
     if (n == 0) return RS_OK;
     RS_CUDA(cudaMemcpyAsync(s->keys[0], h_keys, n * s->key_bytes, cudaMemcpyHostToDevice, st->st), RS_DATA_UPLOAD_FAILED);
     if (s->has_vals) {
@@ -932,13 +1059,22 @@ int rs_sorter_sort_device(rs_sorter s, rs_stream st, const void* d_keys_in, void
     const bool has_vals = d_vals_in != nullptr;
     if (has_vals && (!d_vals_buf0 || (passes > 1 && !d_vals_buf1))) return fail(RS_CALCULATION_FAILED, "null value buffer");
     if (has_vals && n > (1ull << 32)) return fail(RS_CALCULATION_FAILED, "uint32 payload limited to 2^32 keys");
-    RS_CUDA(cudaSetDevice(s->ctx->device), RS_CALCULATION_FAILED);
+    // a pass scatters into tiles other CTAs may still be reading if its source and destination are the same buffer
+    if (d_keys_in == d_keys_buf0 || d_keys_buf0 == d_keys_buf1)
+        return fail(RS_CALCULATION_FAILED, "key buffers alias: only d_keys_in == d_keys_buf1 is allowed");
+    if (has_vals && (d_vals_in == d_vals_buf0 || d_vals_buf0 == d_vals_buf1))
+        return fail(RS_CALCULATION_FAILED, "value buffers alias: only d_vals_in == d_vals_buf1 is allowed");
+    DeviceGuard guard(s->ctx->device); if (guard.status != cudaSuccess) return fail(RS_CALCULATION_FAILED, "cudaSetDevice", guard.status);
     const bool profile = (s->flags & RS_NO_PROFILE) == 0;
     if (profile) {
         int rc = resolve_pending(s, false);
         if (rc != RS_OK) return rc;
     }
     if (n == 0) return RS_OK;
+    if (s->key_bytes == 2)
+        return sort_typed<uint16_t>(s, st->st, static_cast<const uint16_t*>(d_keys_in), static_cast<uint16_t*>(d_keys_buf0),
+                                    static_cast<uint16_t*>(d_keys_buf1), d_vals_in, d_vals_buf0, d_vals_buf1, n, begin_bit,
+                                    end_bit, profile, result_index);
     if (s->key_bytes == 4)
         return sort_typed<uint32_t>(s, st->st, static_cast<const uint32_t*>(d_keys_in), static_cast<uint32_t*>(d_keys_buf0),
                                     static_cast<uint32_t*>(d_keys_buf1), d_vals_in, d_vals_buf0, d_vals_buf1, n, begin_bit,
@@ -954,13 +1090,14 @@ int rs_sorter_sort_segments_device(rs_sorter s, rs_stream st, int num_segments, 
     if (!s || !st || !d_seg_ptrs || !seg_counts) return fail(RS_CALCULATION_FAILED, "null argument");
     if (num_segments < 1 || num_segments > MAX_SEGMENTS) return fail(RS_CALCULATION_FAILED, "1..16 segments supported");
     if (first_segment < 0 || first_segment >= num_segments) return fail(RS_CALCULATION_FAILED, "bad first_segment");
+    if (s->key_bytes < 4) return fail(RS_CALCULATION_FAILED, "the fused gather + sort entry serves 4- and 8-byte keys");
     const int key_bits = static_cast<int>(s->key_bytes) * 8;
     if (begin_bit < 0 || end_bit > key_bits || begin_bit >= end_bit) return fail(RS_CALCULATION_FAILED, "bad bit range");
     const int passes = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
     if (result_index) *result_index = (passes - 1) & 1;
     if (!d_gathered || !d_keys_buf0 || (passes > 1 && !d_keys_buf1)) return fail(RS_CALCULATION_FAILED, "null key buffer");
     if (d_gathered == d_keys_buf0) return fail(RS_CALCULATION_FAILED, "gathered must not alias buf0");
-    RS_CUDA(cudaSetDevice(s->ctx->device), RS_CALCULATION_FAILED);
+    DeviceGuard guard(s->ctx->device); if (guard.status != cudaSuccess) return fail(RS_CALCULATION_FAILED, "cudaSetDevice", guard.status);
     const bool profile = (s->flags & RS_NO_PROFILE) == 0;
     if (profile) {
         int rc = resolve_pending(s, false);
@@ -979,8 +1116,8 @@ int rs_merge_runs_device(rs_context ctx, rs_stream st, rs_key_type type, int num
     if (!ctx || !st || !d_a_ptrs || !a_counts || !d_b_ptrs || !b_counts || !d_out_ptrs || !d_splits)
         return fail(RS_CALCULATION_FAILED, "null argument");
     if (num_jobs < 1 || num_jobs > MERGE_MAX_JOBS) return fail(RS_CALCULATION_FAILED, "1..8 merge jobs per call");
-    if (type < RS_KEY_U32 || type > RS_KEY_I64) return fail(RS_CALCULATION_FAILED, "unknown key type");
-    RS_CUDA(cudaSetDevice(ctx->device), RS_CALCULATION_FAILED);
+    if (type < RS_KEY_U32 || type > RS_KEY_I64) return fail(RS_CALCULATION_FAILED, "the merge serves 32- and 64-bit integer keys");
+    DeviceGuard guard(ctx->device); if (guard.status != cudaSuccess) return fail(RS_CALCULATION_FAILED, "cudaSetDevice", guard.status);
     const bool sg = (type == RS_KEY_I32 || type == RS_KEY_I64);
     if (type == RS_KEY_U32 || type == RS_KEY_I32)
         return merge_runs_typed<uint32_t>(ctx, st->st, sg, num_jobs, d_a_ptrs, a_counts, d_b_ptrs, b_counts, d_out_ptrs, d_splits, splits_capacity);
@@ -990,21 +1127,21 @@ int rs_merge_runs_device(rs_context ctx, rs_stream st, rs_key_type type, int num
 int rs_device_alloc(rs_context ctx, size_t bytes, void** out) {
     if (!ctx || !out) return fail(RS_INITIALIZATION_FAILED, "null argument");
     *out = nullptr;
-    RS_CUDA(cudaSetDevice(ctx->device), RS_INITIALIZATION_FAILED);
+    DeviceGuard guard(ctx->device); if (guard.status != cudaSuccess) return fail(RS_INITIALIZATION_FAILED, "cudaSetDevice", guard.status);
     RS_CUDA(cudaMalloc(out, bytes ? bytes : 1), RS_INITIALIZATION_FAILED);
     return RS_OK;
 }
 int rs_device_free(rs_context ctx, void* p) {
     if (!ctx) return fail(RS_CLEANUP_FAILED, "null argument");
     if (!p) return RS_OK;
-    RS_CUDA(cudaSetDevice(ctx->device), RS_CLEANUP_FAILED);
+    DeviceGuard guard(ctx->device); if (guard.status != cudaSuccess) return fail(RS_CLEANUP_FAILED, "cudaSetDevice", guard.status);
     RS_CUDA(cudaFree(p), RS_CLEANUP_FAILED);
     return RS_OK;
 }
 int rs_ipc_export(rs_context ctx, const void* d_ptr, unsigned char handle[RS_IPC_HANDLE_BYTES]) {
     if (!ctx || !d_ptr || !handle) return fail(RS_INITIALIZATION_FAILED, "null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == RS_IPC_HANDLE_BYTES, "IPC handle size");
-    RS_CUDA(cudaSetDevice(ctx->device), RS_INITIALIZATION_FAILED);
+    DeviceGuard guard(ctx->device); if (guard.status != cudaSuccess) return fail(RS_INITIALIZATION_FAILED, "cudaSetDevice", guard.status);
     cudaIpcMemHandle_t h;
     RS_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)), RS_INITIALIZATION_FAILED);
     memcpy(handle, &h, sizeof h);
@@ -1013,7 +1150,7 @@ int rs_ipc_export(rs_context ctx, const void* d_ptr, unsigned char handle[RS_IPC
 int rs_ipc_open(rs_context ctx, const unsigned char handle[RS_IPC_HANDLE_BYTES], void** out) {
     if (!ctx || !handle || !out) return fail(RS_INITIALIZATION_FAILED, "null argument");
     *out = nullptr;
-    RS_CUDA(cudaSetDevice(ctx->device), RS_INITIALIZATION_FAILED);
+    DeviceGuard guard(ctx->device); if (guard.status != cudaSuccess) return fail(RS_INITIALIZATION_FAILED, "cudaSetDevice", guard.status);
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, sizeof h);
     RS_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess), RS_INITIALIZATION_FAILED);
@@ -1022,7 +1159,7 @@ int rs_ipc_open(rs_context ctx, const unsigned char handle[RS_IPC_HANDLE_BYTES],
 int rs_ipc_close(rs_context ctx, void* p) {
     if (!ctx) return fail(RS_CLEANUP_FAILED, "null argument");
     if (!p) return RS_OK;
-    RS_CUDA(cudaSetDevice(ctx->device), RS_CLEANUP_FAILED);
+    DeviceGuard guard(ctx->device); if (guard.status != cudaSuccess) return fail(RS_CLEANUP_FAILED, "cudaSetDevice", guard.status);
     RS_CUDA(cudaIpcCloseMemHandle(p), RS_CLEANUP_FAILED);
     return RS_OK;
 }
@@ -1047,7 +1184,7 @@ int rs_sorter_download(rs_sorter s, rs_stream st, void* h_keys_out, uint32_t* h_
     if (!s || !st) return fail(RS_DATA_DOWNLOAD_FAILED, "null argument");
     if (!s->keys[0]) return fail(RS_DATA_DOWNLOAD_FAILED, "sorter has no key buffers");
     if (n > s->max_keys) return fail(RS_DATA_DOWNLOAD_FAILED, "n exceeds max_keys");
-    RS_CUDA(cudaSetDevice(s->ctx->device), RS_DATA_DOWNLOAD_FAILED);
+    DeviceGuard guard(s->ctx->device); if (guard.status != cudaSuccess) return fail(RS_DATA_DOWNLOAD_FAILED, "cudaSetDevice", guard.status);
     const int r = s->result_index;
     if (n && h_keys_out)
         RS_CUDA(cudaMemcpyAsync(h_keys_out, s->keys[r], n * s->key_bytes, cudaMemcpyDeviceToHost, st->st),
@@ -1065,7 +1202,7 @@ int rs_sorter_download_async(rs_sorter s, rs_stream st, void* h_keys_out, uint32
     if (!s || !st) return fail(RS_DATA_DOWNLOAD_FAILED, "null argument");
     if (!s->keys[0]) return fail(RS_DATA_DOWNLOAD_FAILED, "sorter has no key buffers");
     if (n > s->max_keys) return fail(RS_DATA_DOWNLOAD_FAILED, "n exceeds max_keys");
-    RS_CUDA(cudaSetDevice(s->ctx->device), RS_DATA_DOWNLOAD_FAILED);
+    DeviceGuard guard(s->ctx->device); if (guard.status != cudaSuccess) return fail(RS_DATA_DOWNLOAD_FAILED, "cudaSetDevice", guard.status);
     const int r = s->result_index;
     if (n && h_keys_out)
         RS_CUDA(cudaMemcpyAsync(h_keys_out, s->keys[r], n * s->key_bytes, cudaMemcpyDeviceToHost, st->st),
@@ -1080,7 +1217,7 @@ int rs_sorter_download_async(rs_sorter s, rs_stream st, void* h_keys_out, uint32
 
 int rs_sorter_download_histograms(rs_sorter s, rs_stream st, uint64_t* h_hist, size_t capacity, int* passes) {
     if (!s || !st || !h_hist) return fail(RS_DATA_DOWNLOAD_FAILED, "null argument");
-    RS_CUDA(cudaSetDevice(s->ctx->device), RS_DATA_DOWNLOAD_FAILED);
+    DeviceGuard guard(s->ctx->device); if (guard.status != cudaSuccess) return fail(RS_DATA_DOWNLOAD_FAILED, "cudaSetDevice", guard.status);
     const int P = s->last_passes;
     if (passes) *passes = P;
     if (P == 0) return RS_OK;
@@ -1095,7 +1232,7 @@ int rs_sorter_last_skipped_passes(rs_sorter s, rs_stream st, int* skipped) {
     if (!s || !st || !skipped) return fail(RS_DATA_DOWNLOAD_FAILED, "null argument");
     *skipped = 0;
     if (s->last_passes == 0) return RS_OK;
-    RS_CUDA(cudaSetDevice(s->ctx->device), RS_DATA_DOWNLOAD_FAILED);
+    DeviceGuard guard(s->ctx->device); if (guard.status != cudaSuccess) return fail(RS_DATA_DOWNLOAD_FAILED, "cudaSetDevice", guard.status);
     SortPlanDev plan{};
     RS_CUDA(cudaMemcpyAsync(&plan, s->scratch + s->last_plan_offset, sizeof plan, cudaMemcpyDeviceToHost, st->st),
             RS_DATA_DOWNLOAD_FAILED);
@@ -1106,7 +1243,7 @@ int rs_sorter_last_skipped_passes(rs_sorter s, rs_stream st, int* skipped) {
 
 int rs_sorter_runtimes(rs_sorter s, rs_runtimes* out) {
     if (!s || !out) return fail(RS_CALCULATION_FAILED, "null argument");
-    RS_CUDA(cudaSetDevice(s->ctx->device), RS_CALCULATION_FAILED);
+    DeviceGuard guard(s->ctx->device); if (guard.status != cudaSuccess) return fail(RS_CALCULATION_FAILED, "cudaSetDevice", guard.status);
     int rc = resolve_pending(s, true);
     if (rc != RS_OK) return rc;
     *out = s->rt;
@@ -1115,7 +1252,7 @@ int rs_sorter_runtimes(rs_sorter s, rs_runtimes* out) {
 
 int rs_sorter_reset_runtimes(rs_sorter s) {
     if (!s) return fail(RS_CALCULATION_FAILED, "null argument");
-    cudaSetDevice(s->ctx->device);
+    DeviceGuard guard(s->ctx->device);
     resolve_pending(s, true);
     stat_reset(s->rt.time_histo); stat_reset(s->rt.time_scan); stat_reset(s->rt.time_reorder);
     stat_reset(s->rt.time_paste); stat_reset(s->rt.time_total);
@@ -1132,37 +1269,38 @@ int rs_dataset_fill_device(rs_context ctx, rs_stream st, rs_key_type type, rs_da
                            uint64_t global_offset, uint64_t total_n, void* d_out, uint64_t n) {
     if (!ctx || !st || (!d_out && n)) return fail(RS_CALCULATION_FAILED, "null argument");
     if (kind < RS_DATASET_ZEROS || kind > RS_DATASET_RANDOM) return fail(RS_CALCULATION_FAILED, "unknown dataset kind");
+    KeyInfo ki{};
+    if (!key_info(type, &ki)) return fail(RS_CALCULATION_FAILED, "unknown key type");
     if (n == 0) return RS_OK;
-    RS_CUDA(cudaSetDevice(ctx->device), RS_CALCULATION_FAILED);
-    const bool sg = (type == RS_KEY_I32 || type == RS_KEY_I64);
-    const int  g  = grid_for(n, 256, ctx->sm_count);
-    if (type == RS_KEY_U32 || type == RS_KEY_I32)
-        rs_fill_kernel<uint32_t><<<g, 256, 0, st->st>>>(static_cast<uint32_t*>(d_out), n, kind, sg, seed, global_offset, total_n);
-    else
-        rs_fill_kernel<uint64_t><<<g, 256, 0, st->st>>>(static_cast<uint64_t*>(d_out), n, kind, sg, seed, global_offset, total_n);
+    DeviceGuard guard(ctx->device);
+    const int g = grid_for(n, 256, ctx->sm_count);
+    for_key_width(ki.bytes, [&](auto u) {
+        using U = decltype(u);
+        rs_fill_kernel<U><<<g, 256, 0, st->st>>>(static_cast<U*>(d_out), n, kind, ki.is_signed, seed, global_offset, total_n);
+    });
     RS_CUDA(cudaGetLastError(), RS_CALCULATION_FAILED);
     return RS_OK;
 }
 
 int rs_check_device(rs_context ctx, rs_stream st, rs_key_type type, const void* d_keys, uint64_t n, uint64_t result[4]) {
     if (!ctx || !st || !result || (!d_keys && n)) return fail(RS_CALCULATION_FAILED, "null argument");
-    RS_CUDA(cudaSetDevice(ctx->device), RS_CALCULATION_FAILED);
-    unsigned long long* d_res = nullptr;
-    RS_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_res), 4 * sizeof(unsigned long long)), RS_CALCULATION_FAILED);
+    KeyInfo ki{};
+    if (!key_info(type, &ki)) return fail(RS_CALCULATION_FAILED, "unknown key type");
+    DeviceGuard guard(ctx->device);
+    std::lock_guard<std::mutex> lock(ctx->result_mutex);
+    unsigned long long* d_res = ctx->d_result;
     cudaMemsetAsync(d_res, 0, 4 * sizeof(unsigned long long), st->st);
     if (n) {
-        const bool sg = (type == RS_KEY_I32 || type == RS_KEY_I64);
-        const int  g  = grid_for(n, 256, ctx->sm_count);
-        if (type == RS_KEY_U32 || type == RS_KEY_I32)
-            rs_check_kernel<uint32_t><<<g, 256, 0, st->st>>>(static_cast<const uint32_t*>(d_keys), n, sg ? 0x80000000u : 0u, d_res);
-        else
-            rs_check_kernel<uint64_t><<<g, 256, 0, st->st>>>(static_cast<const uint64_t*>(d_keys), n,
-                                                            sg ? 0x8000000000000000ull : 0ull, d_res);
+        const int g = grid_for(n, 256, ctx->sm_count);
+        for_key_width(ki.bytes, [&](auto u) {
+            using U = decltype(u);
+            const U sign = ki.is_signed ? static_cast<U>(static_cast<U>(1) << (sizeof(U) * 8 - 1)) : static_cast<U>(0);
+            rs_check_kernel<U><<<g, 256, 0, st->st>>>(static_cast<const U*>(d_keys), n, sign, ki.finf, d_res);
+        });
     }
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(result, d_res, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st->st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st->st);
-    cudaFree(d_res);
     if (e != cudaSuccess) return fail(RS_CALCULATION_FAILED, "rs_check_device", e);
     return RS_OK;
 }
@@ -1170,23 +1308,23 @@ int rs_check_device(rs_context ctx, rs_stream st, rs_key_type type, const void* 
 int rs_check_permutation_device(rs_context ctx, rs_stream st, rs_key_type type, const void* d_keys_in,
                                 const void* d_keys_out, const uint32_t* d_perm, uint64_t n, uint64_t result[2]) {
     if (!ctx || !st || !result) return fail(RS_CALCULATION_FAILED, "null argument");
-    RS_CUDA(cudaSetDevice(ctx->device), RS_CALCULATION_FAILED);
-    unsigned long long* d_res = nullptr;
-    RS_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_res), 2 * sizeof(unsigned long long)), RS_CALCULATION_FAILED);
+    KeyInfo ki{};
+    if (!key_info(type, &ki)) return fail(RS_CALCULATION_FAILED, "unknown key type");
+    DeviceGuard guard(ctx->device);
+    std::lock_guard<std::mutex> lock(ctx->result_mutex);
+    unsigned long long* d_res = ctx->d_result;
     cudaMemsetAsync(d_res, 0, 2 * sizeof(unsigned long long), st->st);
     if (n) {
         const int g = grid_for(n, 256, ctx->sm_count);
-        if (type == RS_KEY_U32 || type == RS_KEY_I32)
-            rs_check_perm_kernel<uint32_t><<<g, 256, 0, st->st>>>(static_cast<const uint32_t*>(d_keys_in),
-                                                                 static_cast<const uint32_t*>(d_keys_out), d_perm, n, d_res);
-        else
-            rs_check_perm_kernel<uint64_t><<<g, 256, 0, st->st>>>(static_cast<const uint64_t*>(d_keys_in),
-                                                                 static_cast<const uint64_t*>(d_keys_out), d_perm, n, d_res);
+        for_key_width(ki.bytes, [&](auto u) {
+            using U = decltype(u);
+            rs_check_perm_kernel<U><<<g, 256, 0, st->st>>>(static_cast<const U*>(d_keys_in), static_cast<const U*>(d_keys_out),
+                                                          d_perm, n, d_res);
+        });
     }
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(result, d_res, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st->st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st->st);
-    cudaFree(d_res);
     if (e != cudaSuccess) return fail(RS_CALCULATION_FAILED, "rs_check_permutation_device", e);
     return RS_OK;
 }
@@ -1194,19 +1332,18 @@ int rs_check_permutation_device(rs_context ctx, rs_stream st, rs_key_type type, 
 int rs_lower_bound_device(rs_context ctx, rs_stream st, rs_key_type type, const void* d_keys, uint64_t n,
                           const void* d_queries, uint64_t num_queries, uint64_t* d_out) {
     if (!ctx || !st || (num_queries && (!d_queries || !d_out))) return fail(RS_CALCULATION_FAILED, "null argument");
+    KeyInfo ki{};
+    if (!key_info(type, &ki) || ki.finf) return fail(RS_CALCULATION_FAILED, "the lower bound serves integer keys");
     if (num_queries == 0) return RS_OK;
-    RS_CUDA(cudaSetDevice(ctx->device), RS_CALCULATION_FAILED);
-    const bool sg = (type == RS_KEY_I32 || type == RS_KEY_I64);
-    const int  g  = grid_for(num_queries, 128, ctx->sm_count);
-    auto* out = reinterpret_cast<unsigned long long*>(d_out);
-    if (type == RS_KEY_U32 || type == RS_KEY_I32)
-        rs_lower_bound_kernel<uint32_t><<<g, 128, 0, st->st>>>(static_cast<const uint32_t*>(d_keys), n,
-                                                              static_cast<const uint32_t*>(d_queries), num_queries,
-                                                              sg ? 0x80000000u : 0u, out);
-    else
-        rs_lower_bound_kernel<uint64_t><<<g, 128, 0, st->st>>>(static_cast<const uint64_t*>(d_keys), n,
-                                                              static_cast<const uint64_t*>(d_queries), num_queries,
-                                                              sg ? 0x8000000000000000ull : 0ull, out);
+    DeviceGuard guard(ctx->device);
+    const int g   = grid_for(num_queries, 128, ctx->sm_count);
+    auto*     out = reinterpret_cast<unsigned long long*>(d_out);
+    for_key_width(ki.bytes, [&](auto u) {
+        using U = decltype(u);
+        const U sign = ki.is_signed ? static_cast<U>(static_cast<U>(1) << (sizeof(U) * 8 - 1)) : static_cast<U>(0);
+        rs_lower_bound_kernel<U><<<g, 128, 0, st->st>>>(static_cast<const U*>(d_keys), n, static_cast<const U*>(d_queries),
+                                                       num_queries, sign, out);
+    });
     RS_CUDA(cudaGetLastError(), RS_CALCULATION_FAILED);
     return RS_OK;
 }

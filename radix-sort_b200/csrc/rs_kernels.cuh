@@ -52,7 +52,8 @@ struct SortPlanDev {
 struct DigitSpec {
     int      shift;  // first bit of the digit
     uint32_t mask;   // (1<<bits)-1
-    uint32_t flip;   // xor applied to the digit (sign bit of signed keys), else 0
+    uint32_t flip;   // xor applied to the digit (sign bit of signed integer keys), else 0
+    unsigned long long finf;  // floating-point keys: bit pattern of +infinity in the key's format; 0 = integer keys
 };
 
 struct PassTable {
@@ -60,8 +61,25 @@ struct PassTable {
     DigitSpec d[MAX_PASSES];
 };
 
+// Floating-point keys (additive, the reference excludes floats, doc/doc.tex:64): the usual
+// order-preserving map of IEEE bit patterns to unsigned integers -- negative values have all bits flipped, the
+// others get the sign bit set -- applied on the fly inside the digit extraction, so keys are stored and moved
+// unmodified and float sorts cost no extra pass.  Every NaN (either sign, any payload) maps to the largest value:
+// NaNs end up last, in input order among themselves, as numpy and torch place them.  -0.0 orders before +0.0.
 template <typename KeyT>
+__device__ __forceinline__ KeyT float_order_bits(KeyT k, unsigned long long finf) {
+    using W = typename std::conditional<sizeof(KeyT) == 8, unsigned long long, uint32_t>::type;
+    constexpr W ALL  = static_cast<W>(~static_cast<KeyT>(0));           // all key bits
+    constexpr W SIGN = static_cast<W>(1) << (sizeof(KeyT) * 8 - 1);
+    const W     w    = static_cast<W>(k);
+    if ((w & (ALL ^ SIGN)) > static_cast<W>(finf)) return static_cast<KeyT>(ALL);
+    return static_cast<KeyT>((w & SIGN) ? (w ^ ALL) : (w | SIGN));
+}
+
+// FK (float keys) is a template parameter of every kernel: integer sorts pay nothing for the transform.
+template <bool FK, typename KeyT>
 __device__ __forceinline__ uint32_t digit_of(KeyT k, const DigitSpec& s) {
+    if constexpr (FK) k = float_order_bits(k, s.finf);
     return (static_cast<uint32_t>(k >> s.shift) & s.mask) ^ s.flip;
 }
 
@@ -155,7 +173,7 @@ struct HistCfg {
     static constexpr size_t bytes = sizeof(uint32_t) * NPASS * RADIX * COLS;
 };
 
-template <typename KeyT, int NPASS>
+template <typename KeyT, int NPASS, bool FK>
 __global__ void __launch_bounds__(HIST_THREADS, 1)
 rs_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ hist /* [NPASS][256] */,
                     PassTable pt) {
@@ -175,7 +193,7 @@ rs_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long lon
     auto count_key = [&](KeyT k) {
 #pragma unroll
         for (int p = 0; p < NPASS; ++p)
-            atomicAdd(&hist_sh[(p * RADIX + digit_of(k, pt.d[p])) * COLS + col], 1u);
+            atomicAdd(&hist_sh[(p * RADIX + digit_of<FK>(k, pt.d[p])) * COLS + col], 1u);
     };
 
     // a block never counts more than 2^32 keys per column (the launcher keeps blocks below 2^31 keys)
@@ -193,7 +211,14 @@ rs_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long lon
 #pragma unroll
         for (int u = 0; u < HIST_VECS; ++u) {
             if (!act[u]) continue;
-            if constexpr (sizeof(KeyT) == 4) {
+            if constexpr (sizeof(KeyT) == 2) {
+                const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    count_key(static_cast<KeyT>(w4[j] & 0xffffu));
+                    count_key(static_cast<KeyT>(w4[j] >> 16));
+                }
+            } else if constexpr (sizeof(KeyT) == 4) {
                 count_key(static_cast<KeyT>(v[u].x));
                 count_key(static_cast<KeyT>(v[u].y));
                 count_key(static_cast<KeyT>(v[u].z));
@@ -279,7 +304,7 @@ rs_gather_histogram_kernel(const SegmentTable<KeyT> seg, KeyT* __restrict__ gath
                     dst[i] = v[u];
 #pragma unroll
                     for (int p = 0; p < NPASS; ++p)
-                        atomicAdd(&hist_sh[(p * RADIX + digit_of(v[u], pt.d[p])) * COLS + col], 1u);
+                        atomicAdd(&hist_sh[(p * RADIX + digit_of<false>(v[u], pt.d[p])) * COLS + col], 1u);
                 }
             }
         }
@@ -421,7 +446,7 @@ __device__ __forceinline__ uint32_t atoms_add_return(uint32_t* p, uint32_t v) {
     return old;
 }
 
-template <typename KeyT, bool HAS_VALS, int THREADS, int KPT, int MIN_BLOCKS, bool ATOMIC_RANK>
+template <typename KeyT, bool HAS_VALS, int THREADS, int KPT, int MIN_BLOCKS, bool ATOMIC_RANK, bool FK>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
     using L = OnesweepSmem<KeyT, HAS_VALS, THREADS, KPT, ATOMIC_RANK>;
@@ -540,7 +565,7 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
         uint32_t uniform_rows = 0;                       // atomic mode: bit r = all 32 digits of row r are equal
 #pragma unroll
         for (int r = 0; r < KPT; ++r) {
-            uint32_t d = digit_of(key[r], ds);
+            uint32_t d = digit_of<FK>(key[r], ds);
             if (!FULL && (my_first + ROW * r) >= valid) d = RADIX - 1;  // padding ranks last
             if constexpr (ATOMIC_RANK) {
                 int all_same;
@@ -621,7 +646,7 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
         // ---- scatter into shared memory in ranked order -----------------------------------------
 #pragma unroll
         for (int r = 0; r < KPT; ++r) {
-            uint32_t d = digit_of(key[r], ds);
+            uint32_t d = digit_of<FK>(key[r], ds);
             if (!FULL && (my_first + ROW * r) >= valid) d = RADIX - 1;
             uint32_t pos;
             if constexpr (ATOMIC_RANK) {
@@ -691,7 +716,7 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
             const uint32_t p = i * THREADS + tid;
             if (FULL || p < valid) {
                 const KeyT     k = stg[swz(p)];
-                const uint32_t d = digit_of(k, ds);
+                const uint32_t d = digit_of<FK>(k, ds);
                 kptr[d][p]       = k;
                 if constexpr (HAS_VALS) vptr[d][p] = vstage[swz(p)];
             }
@@ -735,7 +760,7 @@ struct SmallSmem {
     static constexpr size_t total    = off_wsum + sizeof(uint32_t) * 16;
 };
 
-template <typename KeyT, bool HAS_VALS>
+template <typename KeyT, bool HAS_VALS, bool FK>
 __global__ void __launch_bounds__(SMALL_THREADS, 1)
 rs_small_sort_kernel(const KeyT* in, KeyT* out, const uint32_t* vin, uint32_t* vout,  // `out` may alias `in`
                      uint32_t n, PassTable pt, unsigned long long* __restrict__ hist,
@@ -771,7 +796,7 @@ rs_small_sort_kernel(const KeyT* in, KeyT* out, const uint32_t* vin, uint32_t* v
             const uint32_t i = my_first + 32 * r;
             key[r]           = kbuf[cur * SMALL_CAP + i];
             if constexpr (HAS_VALS) val[r] = vbuf[cur * SMALL_CAP + i];
-            const uint32_t d = (i < n) ? digit_of(key[r], ds) : RADIX - 1;  // padding sits past n and ranks last
+            const uint32_t d = (i < n) ? digit_of<FK>(key[r], ds) : RADIX - 1;  // padding sits past n and ranks last
             int all_same;
             __match_all_sync(0xffffffffu, d, &all_same);
             if (all_same) {
@@ -820,7 +845,7 @@ rs_small_sort_kernel(const KeyT* in, KeyT* out, const uint32_t* vin, uint32_t* v
 #pragma unroll
         for (int r = 0; r < SMALL_KPT; ++r) {
             const uint32_t i = my_first + 32 * r;
-            const uint32_t d = (i < n) ? digit_of(key[r], ds) : RADIX - 1;
+            const uint32_t d = (i < n) ? digit_of<FK>(key[r], ds) : RADIX - 1;
             uint32_t pos;
             if (uniform_rows & (1u << r)) {
                 uint32_t c = 0;

@@ -6,11 +6,11 @@ tensors are the sorter's ping-pong buffers themselves (no copy); ``indices`` is 
 (``torch.sort(stable=True)`` semantics), stored as int32 bit patterns of the library's uint32 payload, so inputs
 are limited to 2^31 - 1 keys when indices are requested.
 
-float32 / float64 keys (additive: the reference excludes floats, doc/doc.tex:64) are sorted through the
-usual order-preserving bit transform -- flip the magnitude bits of negative values, then sort as signed integers --
-applied with two elementwise torch ops around the integer sort; the C ABI itself stays integer-only.  Order is the
-IEEE total order of the bit patterns: -NaN < -inf < ... < -0.0 < +0.0 < ... < +inf < +NaN.
-int16 / uint16 keys are widened to 32 bits and sorted on bits 0..15 only (two passes instead of four).
+Every dtype is a key type of the C ABI (include/rsb200.h rs_key_type): (u)int16/32/64 and -- additive, the
+reference excludes floats (doc/doc.tex:64) -- float16 / bfloat16 / float32 / float64.  Floating-point keys are
+ordered by value inside the kernels' digit extraction (no conversion passes around the sort):
+-inf < ... < -0.0 < +0.0 < ... < +inf < NaN, every NaN last and in input order, as torch.sort places them.
+16-bit keys take two onesweep passes, 32-bit keys four, 64-bit keys eight.
 
 There is no CPU fallback: a tensor that is not on a CUDA device, or a missing ``librsb200.so``, raises.
 The reference has no counterpart (its user entry is examples/basic_sort/basic_sort.cpp:24-139, host buffers only).
@@ -21,14 +21,9 @@ import threading
 
 from . import capi
 
-_KEY_OF_DTYPE = {"torch.int32": "i32", "torch.int64": "i64", "torch.uint32": "u32", "torch.uint64": "u64"}
-_INT_OF_FLOAT = {"torch.float32": ("int32", 31), "torch.float64": ("int64", 63)}
-_BIAS_OF_NARROW = {"torch.int16": 1 << 15, "torch.uint16": 0}   # 16-bit keys: widened, biased to 0..65535, two passes
-
-
-def _float_to_ordered(bits, sign_shift: int):
-    """Signed-integer view of IEEE bits -> signed integers in the same order (its own inverse)."""
-    return bits ^ ((bits >> sign_shift) & ((1 << sign_shift) - 1))   # arithmetic shift: all-ones mask for negatives
+_KEY_OF_DTYPE = {"torch.int32": "i32", "torch.int64": "i64", "torch.uint32": "u32", "torch.uint64": "u64",
+                 "torch.int16": "i16", "torch.uint16": "u16", "torch.float32": "f32", "torch.float64": "f64",
+                 "torch.float16": "f16", "torch.bfloat16": "bf16"}
 
 
 class _NativeBackend:
@@ -69,22 +64,9 @@ class TorchSorter:
 
     def sort(self, keys, return_indices: bool = True, end_bit: int | None = None):
         import torch
-        bias = _BIAS_OF_NARROW.get(str(keys.dtype))
-        if bias is not None:
-            if keys.dim() != 1 or not keys.is_contiguous():
-                raise ValueError("keys must be a contiguous 1-D tensor")
-            wide, indices = self.sort(keys.to(torch.int32) + bias, return_indices, end_bit=16)   # digits of bits 0..15 only
-            return (wide - bias).to(keys.dtype), indices
-        as_float = _INT_OF_FLOAT.get(str(keys.dtype))
-        if as_float is not None:
-            if keys.dim() != 1 or not keys.is_contiguous():
-                raise ValueError("keys must be a contiguous 1-D tensor")
-            int_dtype, sign_shift = getattr(torch, as_float[0]), as_float[1]
-            ordered, indices = self.sort(_float_to_ordered(keys.view(int_dtype), sign_shift), return_indices)
-            return _float_to_ordered(ordered, sign_shift).view(keys.dtype), indices
         key_type = _KEY_OF_DTYPE.get(str(keys.dtype))
         if key_type is None:
-            raise TypeError(f"unsupported key dtype {keys.dtype}: (u)int16, (u)int32, (u)int64, float32, float64")
+            raise TypeError(f"unsupported key dtype {keys.dtype}: (u)int16/32/64, float16, bfloat16, float32, float64")
         if keys.dim() != 1 or not keys.is_contiguous():
             raise ValueError("keys must be a contiguous 1-D tensor")
         if self.backend.__class__ is _NativeBackend and not keys.is_cuda:
@@ -120,7 +102,7 @@ _per_device: dict[int, TorchSorter] = {}
 
 
 def sort(keys, return_indices: bool = True):
-    """Ascending sort of a 1-D CUDA tensor of int32/int64/uint32/uint64 (or float32/float64, see the module text) keys.
+    """Ascending sort of a 1-D CUDA tensor of (u)int16/32/64 or float16/bfloat16/float32/float64 keys.
 
     Returns ``(values, indices)``; ``indices`` (int32) is the stable permutation with ``keys[indices] == values``,
     or ``None`` when ``return_indices`` is False (keys-only sorts run ~1.7x faster).  The work is enqueued on

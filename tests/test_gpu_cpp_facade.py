@@ -35,6 +35,16 @@ def test_icompute_task_flow_all_types_all_datasets(n):
     assert all(int(r.split(",")[0]) == n for r in rows)
 
 
+def test_icompute_task_flow_16_bit_types():
+    # the other two rows of the reference's type table as native key types of the C ABI
+    out = _run([RUNNER, "--num-elements", str(1 << 18), "--narrow-types", "--perf-csv-to-stdout"])
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert out.stdout.count("GOLD TEST PASSED!") == 30
+    assert out.stdout.count("Validation of GPU permutation (stable argsort) has passed") == 30
+    rows = [l for l in out.stdout.splitlines() if l and l[0].isdigit() and l.count(",") >= 9]
+    assert {"uint16_t", "int16_t"} <= {r.split(",")[1] for r in rows}
+
+
 def test_icompute_task_flow_ragged_size():
     # N not a multiple of 1024: the task sorts the rounded buffer (data + zero tail, src/CRadixSortTask.cpp:176)
     # and compares the first N.  The GPU path and its permutation must validate for every type and dataset;

@@ -469,7 +469,7 @@ def test_merge_tree_levels(rsb, gpu, t, n_runs):
 
 # ---- BASELINE.json full sizes: size-independent properties, everything resident on the device -------
 
-def _full_size_case(rsb, gpu, t, kind, n, with_perm):
+def _full_size_case(rsb, gpu, t, kind, n, with_perm, flags=0):
     torch = _torch()
     ctx, st = gpu
     tdt = torch.int32 if numpy_dtype(t).itemsize == 4 else torch.int64
@@ -481,7 +481,7 @@ def _full_size_case(rsb, gpu, t, kind, n, with_perm):
         vb = [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(2)]
     torch.cuda.synchronize()
     ctx.fill_dataset(st, t, kind, d_in.data_ptr(), n, seed=SEED)
-    s = rsb.Sorter(ctx, t, n, rsb.RS_NO_KEY_BUFFERS)
+    s = rsb.Sorter(ctx, t, n, rsb.RS_NO_KEY_BUFFERS | flags)
     r = s.sort_device(st, d_in.data_ptr(), bufs[0].data_ptr(), bufs[1].data_ptr(), n,
                       vin.data_ptr() if with_perm else None, vb[0].data_ptr() if with_perm else None,
                       vb[1].data_ptr() if with_perm else None)
@@ -516,6 +516,205 @@ def test_full_size_2_28_u32_key_value(rsb, gpu, kind):
 @pytest.mark.parametrize("kind", ("uniform", "inverted", "random"))
 def test_full_size_2_28_other_types(rsb, gpu, t, kind):
     _full_size_case(rsb, gpu, t, kind, 1 << 28, with_perm=False)          # configs[3]
+
+
+# ---- the other rows of the reference's type table (int16_t / uint16_t, Common/CLTypeInformation.h:12-22)
+#      and floating-point keys as NATIVE key types of the C ABI (no conversion passes) ------------------------------------
+
+def _sort_any(rsb, gpu, keys, t, with_perm, flags=0):
+    ctx, st = gpu
+    n = len(keys)
+    s = rsb.Sorter(ctx, t, max(n, 1), flags | (rsb.RS_WITH_PERMUTATION if with_perm else 0))
+    try:
+        s.upload(st, keys, None, n)
+        s.sort(st, n)
+        out = np.empty(n, dtype=keys.dtype)
+        perm = np.empty(n, dtype=np.uint32) if with_perm else None
+        s.download(st, out, perm, n)
+        return out, perm, s.download_histograms(st)
+    finally:
+        s.close()
+
+
+@pytest.mark.parametrize("t", ("u16", "i16"))
+@pytest.mark.parametrize("mode", ("atomic", "bitmap"))
+def test_16_bit_keys_native(rsb, gpu, t, mode):
+    dt = rsb.key_dtype(t)
+    info = np.iinfo(dt)
+    rng = np.random.default_rng(41)
+    flags = rsb.RS_NO_ATOMIC_RANK if mode == "bitmap" else 0
+    for n in (1, 7, 4096, 4097, 100_003, (1 << 21) + 5):
+        for lo, hi in ((info.min, info.max), (0, 3)):
+            data = rng.integers(lo, hi, size=n, dtype=dt, endpoint=True)
+            got, perm, hist = _sort_any(rsb, gpu, data, t, True, flags)
+            order = np.argsort(data, kind="stable")
+            assert np.array_equal(got, data[order]), (t, n)
+            assert np.array_equal(perm.astype(np.int64), order), (t, n)
+            assert hist.shape == (2, 256)       # two 8-bit digits: two passes
+    ctx, st = gpu
+    s = rsb.Sorter(ctx, t, 2048)
+    s.pad(st, 1000, 2048)                       # max - 1, src/RadixSortGPU.cpp:274-276
+    s.sort(st, 2048)
+    out = np.empty(2048, dtype=dt)
+    s.download(st, out, None, 2048)
+    assert (out[-1048:] == info.max - 1).all()
+    s.close()
+
+
+def _float_order_key(bits, inf_bits):
+    """The order rsb200.h documents for float keys, on unsigned bit patterns: by value, -0.0 < +0.0, every NaN last."""
+    nbits = bits.itemsize * 8
+    u = bits.astype(np.uint64)
+    sign, allb = np.uint64(1 << (nbits - 1)), np.uint64((1 << nbits) - 1)
+    key = np.where((u & sign) != 0, u ^ allb, u | sign)
+    return np.where((u & (allb ^ sign)) > np.uint64(inf_bits), allb, key)
+
+
+@pytest.mark.parametrize("t,udt,inf_bits", [("f32", np.uint32, 0x7f800000), ("f64", np.uint64, 0x7ff0000000000000),
+                                            ("f16", np.uint16, 0x7c00), ("bf16", np.uint16, 0x7f80)])
+def test_float_keys_native(rsb, gpu, t, udt, inf_bits):
+    dt = rsb.key_dtype(t)
+    rng = np.random.default_rng(42)
+    nbits = np.dtype(udt).itemsize * 8
+    sign = 1 << (nbits - 1)
+    specials = np.array([0, sign, inf_bits, inf_bits | sign, inf_bits + 1, (inf_bits + 1) | sign, (1 << nbits) - 1, 1, sign | 1,
+                         inf_bits - 1, (inf_bits - 1) | sign], dtype=udt)   # +-0, +-inf, NaNs of both signs, denormals, +-max
+    for n in (11, 4000, 250_007, (1 << 20) + 3):
+        bits = rng.integers(0, (1 << nbits) - 1, size=n, dtype=udt, endpoint=True)   # every class of value, NaNs included
+        bits[: len(specials)] = specials
+        if n > 100_000:
+            bits[n // 2:] = rng.choice(specials, size=n - n // 2)                    # heavy ties: stability
+        data = bits.view(dt)
+        got, perm, hist = _sort_any(rsb, gpu, data, t, True)
+        order = np.argsort(_float_order_key(bits, inf_bits), kind="stable")
+        assert np.array_equal(got.view(udt), bits[order]), (t, n)                    # bit-exact, NaN payloads included
+        assert np.array_equal(perm.astype(np.int64), order), (t, n)
+        assert hist.shape == (nbits // 8, 256)
+        if dt.kind == "f":   # the same VALUES as numpy's sort (NaNs last; numpy does not tell -0.0 from +0.0)
+            assert np.array_equal(got, np.sort(data), equal_nan=True), (t, n)
+    ctx, st = gpu
+    d = rng.integers(0, (1 << nbits) - 1, size=1 << 16, dtype=udt, endpoint=True)
+    import torch
+    dev = torch.from_numpy(d.view(np.int16 if nbits == 16 else np.int32 if nbits == 32 else np.int64).copy()).cuda()
+    torch.cuda.synchronize()
+    assert ctx.check(st, t, dev.data_ptr(), d.size)["unordered"] > 0                 # the device check knows the float order
+    got, _, _ = _sort_any(rsb, gpu, d.view(dt), t, False)
+    dev.copy_(torch.from_numpy(got.view(np.int16 if nbits == 16 else np.int32 if nbits == 32 else np.int64).copy()))
+    torch.cuda.synchronize()
+    assert ctx.check(st, t, dev.data_ptr(), d.size)["unordered"] == 0
+
+
+def test_integer_only_entries_reject_float_keys(rsb, gpu):
+    ctx, st = gpu
+    with pytest.raises(rsb.RsError):
+        ctx.lower_bound(st, "f32", 0, 0, 1, 1, 1)
+    with pytest.raises(rsb.RsError):
+        ctx.merge_runs(st, "f32", [(1, 1, 1, 1, 1)], 1, 16)
+    with pytest.raises(rsb.RsError):
+        ctx.merge_runs(st, "u16", [(1, 1, 1, 1, 1)], 1, 16)
+
+
+def test_sort_device_rejects_aliased_buffers(rsb, gpu):
+    torch = _torch()
+    ctx, st = gpu
+    a, b = (torch.zeros(1024, dtype=torch.int32, device="cuda") for _ in range(2))
+    s = rsb.Sorter(ctx, "u32", 1024, rsb.RS_NO_KEY_BUFFERS)
+    with pytest.raises(rsb.RsError):
+        s.sort_device(st, a.data_ptr(), a.data_ptr(), b.data_ptr(), 1024)     # in == buf0
+    with pytest.raises(rsb.RsError):
+        s.sort_device(st, a.data_ptr(), b.data_ptr(), b.data_ptr(), 1024)     # buf0 == buf1
+    s.sort_device(st, a.data_ptr(), b.data_ptr(), a.data_ptr(), 1024)         # in == buf1: the documented double buffer
+    st.sync()
+    s.close()
+
+
+# ---- BASELINE.json configs[1..3] at FULL size, EXACT: inputs from the reference's own generators (mt19937 /
+#      uniform_int_distribution streams, oracle.dataset == src/Dataset.h:84-137), sorted through the reference-facing
+#      upload -> sort -> download calls and compared byte for byte with np.sort -- what CRadixSortTask::ValidateResults
+#      asserts with memcmp against std::sort (src/CRadixSortTask.cpp:225-252, tests/tests.cpp:18-28) ------------------
+
+def _assert_stable_permutation(data, got, perm):
+    """perm is THE stable sorting permutation of data (given got == sort(data)): gathers to got, and is increasing
+    inside every run of equal keys -- which also makes it a bijection."""
+    assert perm.dtype == np.uint32 and int(perm.max()) < len(data)
+    assert np.array_equal(data[perm], got)
+    eq = got[1:] == got[:-1]
+    assert bool((perm[1:][eq] > perm[:-1][eq]).all())
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_exact_2_28_u32_reference_datasets(rsb, gpu, oracle, kind):
+    data = oracle.dataset(kind, "u32", 1 << 28, SEED)
+    got, _, _ = host_sort(rsb, gpu, data, "u32")
+    assert got.tobytes() == np.sort(data).tobytes(), kind
+
+
+@pytest.mark.parametrize("kind,flags", [("random", 0), ("uniform", "bitmap")])
+def test_exact_2_28_u32_key_index(rsb, gpu, oracle, kind, flags):
+    # configs[2]: keys + stable permutation at full size, default ranking mode and the lane-bitmap fallback;
+    # 2^28 draws of a 32-bit generator hold ~2^23 duplicate pairs, so stability is exercised
+    data = oracle.dataset(kind, "u32", 1 << 28, SEED)
+    got, perm, _ = host_sort(rsb, gpu, data, "u32", with_perm=True, flags=rsb.RS_NO_ATOMIC_RANK if flags else 0)
+    assert got.tobytes() == np.sort(data).tobytes()
+    _assert_stable_permutation(data, got, perm)
+
+
+@pytest.mark.parametrize("t,kind", [("i64", "uniform"), ("i32", "random")])
+def test_exact_2_28_signed_and_wide_keys(rsb, gpu, oracle, t, kind):
+    # configs[3]: sign-bit flip and 8-byte keys at full size, exact
+    data = oracle.dataset(kind, t, 1 << 28, SEED)
+    got, _, _ = host_sort(rsb, gpu, data, t)
+    assert got.tobytes() == np.sort(data).tobytes()
+
+
+@pytest.mark.parametrize("flags", [0, "bitmap"])
+def test_full_size_2_28_u64_key_value_both_modes(rsb, gpu, flags):
+    # 8-byte keys + index at full size in both ranking modes (in-situ evidence for the lane-order property the default
+    # mode rests on: any out-of-order service of same-word atomics shows up as a stability violation here)
+    _full_size_case(rsb, gpu, "u64", "uniform", 1 << 28, with_perm=True, flags=rsb.RS_NO_ATOMIC_RANK if flags else 0)
+    _full_size_case(rsb, gpu, "u64", "random", 1 << 28, with_perm=True, flags=rsb.RS_NO_ATOMIC_RANK if flags else 0)
+
+
+# ---- transfer stage (SURVEY.md 8(f).2, src/RadixSortGPU.cpp:365-429): pinned host buffers, asynchronous download,
+#      several sorters on several streams -- the call pattern bench.py's `e2e` runs on -----------------------------------
+
+@pytest.mark.parametrize("t,with_perm", [("u32", False), ("i64", True)])
+def test_pinned_async_lanes_bit_exact(rsb, gpu, oracle, t, with_perm):
+    ctx, _ = gpu
+    n, lanes_n, batches = (1 << 22) + 4321, 3, 7
+    dt = numpy_dtype(t)
+    flags = rsb.RS_WITH_PERMUTATION if with_perm else 0
+    lanes = [dict(s=rsb.Sorter(ctx, t, n, flags), st=rsb.Stream(ctx), hin=rsb.HostBuffer(n, dt), hout=rsb.HostBuffer(n, dt),
+                  hperm=rsb.HostBuffer(n, np.uint32) if with_perm else None, batch=None) for _ in range(lanes_n)]
+    inputs = [oracle.dataset(("uniform", "random", "inverted")[b % 3], t, n, SEED + b) for b in range(batches)]
+
+    def verify(lane):
+        b = lane["batch"]
+        if b is None:
+            return
+        lane["st"].sync()                      # the lane's previous batch (its pinned buffers) is complete
+        got = lane["hout"].array
+        assert np.array_equal(got, np.sort(inputs[b])), (t, b)
+        if with_perm:
+            _assert_stable_permutation(inputs[b], got, lane["hperm"].array)
+        got[:] = 0                             # a stale buffer must not pass for the next batch
+
+    try:
+        for b in range(batches):
+            lane = lanes[b % lanes_n]
+            verify(lane)
+            lane["hin"].array[:] = inputs[b]
+            lane["s"].upload(lane["st"], lane["hin"], None, n)
+            lane["s"].sort(lane["st"], n)
+            lane["s"].download_async(lane["st"], lane["hout"], lane["hperm"], n)   # returns at once: nothing is synchronised here
+            lane["batch"] = b
+        for lane in lanes:
+            verify(lane)
+    finally:
+        for lane in lanes:
+            lane["s"].close(); lane["st"].close(); lane["hin"].close(); lane["hout"].close()
+            if lane["hperm"] is not None:
+                lane["hperm"].close()
 
 
 def test_lookback_chunk_handover_exact(tmp_path):
@@ -582,8 +781,43 @@ def test_torch_sort_operator_float_keys(rsb):
         assert np.array_equal(got, np.sort(host)) and np.array_equal(host[indices.cpu().numpy()], got)
 
 
+def test_torch_sort_operator_half_and_nan(rsb):
+    import importlib
+    op = importlib.import_module("radix-sort_b200.torch_op")
+    torch = _torch()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for dt in (torch.float16, torch.bfloat16, torch.float32):
+        keys = (torch.randn(300_000, device="cuda", generator=g) * 100).to(dt)
+        keys[::1000] = float("nan")
+        keys[1::1000] = float("-inf")
+        values, indices = op.sort(keys)
+        ref_v, ref_i = torch.sort(keys, stable=True)       # torch: NaNs last, stable -- the same placement
+        torch.cuda.synchronize()
+        assert torch.equal(values.isnan(), ref_v.isnan())
+        assert torch.equal(values[~values.isnan()], ref_v[~ref_v.isnan()])
+        assert torch.equal(keys[indices.long()].isnan(), values.isnan())
+        assert torch.equal(keys[indices.long()][~values.isnan()], values[~values.isnan()])
+
+
+@pytest.mark.parametrize("dt_name", ["int16", "uint16"])
+def test_torch_sort_operator_16_bit_keys(rsb, dt_name):
+    import importlib
+    op = importlib.import_module("radix-sort_b200.torch_op")
+    torch = _torch()
+    np_dt = np.dtype(dt_name)
+    info = np.iinfo(np_dt)
+    host = np.random.default_rng(24).integers(info.min, info.max, size=700_001, dtype=np_dt, endpoint=True)
+    keys = torch.from_numpy(host.view(np.int16).copy()).cuda().view(getattr(torch, dt_name))
+    values, indices = op.sort(keys)
+    torch.cuda.synchronize()
+    order = np.argsort(host, kind="stable")
+    assert values.dtype == getattr(torch, dt_name)
+    assert np.array_equal(values.view(torch.int16).cpu().numpy().view(np_dt), host[order])
+    assert np.array_equal(indices.cpu().numpy().astype(np.int64), order)
+
+
 def test_torch_sort_operator_int16_keys(rsb):
-    # 16-bit keys: widened and sorted on bits 0..15 only, i.e. two onesweep passes (torch_op.py)
+    # 16-bit keys are a native key type: two onesweep passes over 2-byte keys
     import importlib
     op = importlib.import_module("radix-sort_b200.torch_op")
     torch = _torch()

@@ -19,7 +19,9 @@ class _FakeSorter:
     created = []
 
     def __init__(self, key_type, capacity):
-        self.np_dt = {"u32": np.uint32, "i32": np.int32, "u64": np.uint64, "i64": np.int64}[key_type]
+        self.np_dt = {"u32": np.uint32, "i32": np.int32, "u64": np.uint64, "i64": np.int64, "u16": np.uint16, "i16": np.int16,
+                      "f32": np.float32, "f64": np.float64, "f16": np.float16, "bf16": np.uint16}[key_type]
+        self.key_type = key_type
         self.capacity, self.closed = capacity, False
         _FakeSorter.created.append(self)
 
@@ -31,6 +33,14 @@ class _FakeSorter:
         keys = self._view(d_in, n, self.np_dt)
         bits = self.np_dt().itemsize * 8 if end_bit is None else end_bit
         digits = keys if end_bit is None else (keys.astype(np.int64) & ((1 << bits) - 1))   # only bits [0, end_bit) order the keys
+        if self.key_type[0] == "f" or self.key_type == "bf16":
+            # the library's float order (include/rsb200.h): by value, -0.0 before +0.0, every NaN last
+            u = keys.view({2: np.uint16, 4: np.uint32, 8: np.uint64}[keys.itemsize]).astype(np.uint64)
+            nbits = keys.itemsize * 8
+            sign, allb = np.uint64(1 << (nbits - 1)), np.uint64((1 << nbits) - 1)
+            inf = np.uint64({"f16": 0x7c00, "bf16": 0x7f80, "f32": 0x7f800000, "f64": 0x7ff0000000000000}[self.key_type])
+            digits = np.where((u & sign) != 0, u ^ allb, u | sign)
+            digits = np.where((u & (allb ^ sign)) > inf, allb, digits)
         order = np.argsort(digits, kind="stable")
         self._view(d_buf1, n, self.np_dt)[:] = keys[order]
         self._view(d_buf0, n, self.np_dt)[:] = 0
@@ -100,9 +110,19 @@ def test_float_keys_total_order(op):
         z = np.flatnonzero(got == 0.0)
         assert np.signbit(got[z[0]]) and not np.signbit(got[z[-1]])    # -0.0 before +0.0
         assert torch.equal(keys, torch.from_numpy(host))               # input untouched
-        with_nan = torch.tensor([1.0, float("nan"), -2.0, float("inf")], dtype=dt)
-        v, _ = ts.sort(with_nan)
-        assert torch.isnan(v[-1]) and v[0].item() == -2.0 and torch.isinf(v[-2])
+        with_nan = torch.tensor([1.0, float("nan"), -2.0, float("inf"), -float("nan")], dtype=dt)
+        v, idx = ts.sort(with_nan)
+        assert torch.isnan(v[-1]) and torch.isnan(v[-2]) and v[0].item() == -2.0 and torch.isinf(v[-3])
+        assert idx.tolist() == [2, 0, 3, 1, 4]                         # NaNs of either sign last, in input order
+    ts.close()
+
+
+def test_half_precision_keys(op):
+    ts = op.TorchSorter(0, backend=_FakeBackend())
+    for dt in (torch.float16, torch.bfloat16):
+        keys = torch.tensor([3.5, -1.0, float("inf"), 0.0, -0.0, float("nan"), -float("inf"), 2.0], dtype=dt)
+        values, indices = ts.sort(keys)
+        assert values.dtype == dt and indices.tolist() == [6, 1, 4, 3, 7, 0, 2, 5]
     ts.close()
 
 
@@ -125,7 +145,7 @@ def test_16_bit_keys_two_passes(op):
 def test_argument_checks(op):
     ts = op.TorchSorter(0, backend=_FakeBackend())
     with pytest.raises(TypeError):
-        ts.sort(torch.zeros(4, dtype=torch.float16))
+        ts.sort(torch.zeros(4, dtype=torch.complex64))
     with pytest.raises(ValueError):
         ts.sort(torch.zeros((2, 2), dtype=torch.int32))
     with pytest.raises(ValueError):

@@ -8,7 +8,12 @@ def main():
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
     rows = list(csv.reader(open(path)))
     hdr = rows[1]
-    data = [r for r in rows[2:] if len(r) >= len(hdr) - 2]
+    body = rows[2:]
+    for k, r in enumerate(body):          # several launches in one export: keep the first
+        if r and r[0] == "Kernel Name":
+            body = body[:k]
+            break
+    data = [r for r in body if len(r) >= len(hdr) - 2]
     ci = {h: i for i, h in enumerate(hdr)}
     samp = ci["# Samples"]
     stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
