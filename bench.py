@@ -392,9 +392,13 @@ def bench_distributed(args):
     n_local = total // world
     ctx = rsb.Context(local_rank)
     st = rsb.Stream(ctx, torch.cuda.current_stream().cuda_stream)
-    ops = dsort.CudaOps(rsb, ctx, st, KEY_TYPE, n_local + n_local // 8 + (1 << 20))
     cap = n_local + n_local // 8 + (1 << 20)
     exchange = args.exchange
+    native = None
+    if exchange == "native":
+        # the product path: rs_dist_create_rank / rs_dist_sort (C ABI): NCCL, peer mapping, splitters and merge tree inside
+        native = dsort.NativeDistSort(rsb, ctx, st, KEY_TYPE, n_local + 1024, dist)
+    ops = dsort.CudaOps(rsb, ctx, st, KEY_TYPE, (n_local + n_local // 8 + (1 << 20)) if native is None else 1024)
     ops.final_step = args.final   # "merge": pairwise merge tree over peer memory, "sort": fused pull + histogram + onesweep passes
     if exchange == "p2p":
         # fused NVLink pull + histogram kernel instead of NCCL all-to-all; every rank must be able to map every peer
@@ -423,13 +427,16 @@ def bench_distributed(args):
     if parity_failures:
         raise RuntimeError(f"bench: distributed sort failed exact parity in {parity_failures} of {parity_cases} cases")
     shard = ops.empty(n_local)
-    scratch = {k: ops.empty(cap) for k in (("recv", "c") if exchange == "p2p" else ("a", "b", "recv", "c"))}
+    scratch = {} if native is not None else {k: ops.empty(cap) for k in (("recv", "c") if exchange == "p2p" else ("a", "b", "recv", "c"))}
     ctx.fill_dataset(st, KEY_TYPE, args.dataset, shard.data_ptr(), n_local, seed=0x5EED,
                      global_offset=rank * n_local, total_n=total)
     before = ctx.check(st, KEY_TYPE, shard.data_ptr(), n_local)
 
-    def step():
-        return dsort.distributed_sort(shard, ops, dist, KEY_TYPE, scratch=scratch)
+    def step(src=None):
+        src = shard if src is None else src
+        if native is not None:
+            return native.sort(src)
+        return dsort.distributed_sort(src, ops, dist, KEY_TYPE, scratch=scratch)
 
     for _ in range(max(args.warmup, 3)):
         out = step()
@@ -439,7 +446,6 @@ def bench_distributed(args):
     if sampler:
         sampler.start()
         time.sleep(0.25)
-    l0 = ops.sorter.launch_count
     dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -450,7 +456,10 @@ def bench_distributed(args):
     torch.cuda.synchronize()
     dist.barrier()
     ms = e0.elapsed_time(e1) / args.steps
-    launches = ops.sorter.launch_count - l0
+    # kernels of one sort per GPU: memset-free count of the launches rs_dist_sort / distributed_sort enqueue
+    levels_ = max(1, (world - 1).bit_length())
+    split_rounds = 3   # 32-bit keys: 11 + 11 + 10 bits
+    launches = args.steps * ((2 + PASSES) + 3 * split_rounds + 3 + 3 * levels_)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
@@ -477,17 +486,11 @@ def bench_distributed(args):
         return bool(ok)
 
     # ---- one instrumented step: device time of every stage (CUDA events; the headline above runs without them) ----
-    ops.stage_events = []
-    step()
-    torch.cuda.synchronize()
-    stages = {}
-    for name, a, b in ops.stage_events:
-        stages[name] = stages.get(name, 0.0) + a.elapsed_time(b)
-    ops.stage_events = None
-    st_t = torch.tensor([stages.get(k, 0.0) for k in ("local_sort", "splitters", "merge_level_1", "merge_levels_local", "final_sort", "closing")],
-                        dtype=torch.float64, device="cuda")
+    stage_names = ("local_sort", "splitters", "merge_level_1", "merge_levels_local", "closing", "total")
+    stages = native.stage_ms() if native is not None else {}
+    st_t = torch.tensor([stages.get(k, 0.0) for k in stage_names], dtype=torch.float64, device="cuda")
     dist.all_reduce(st_t, op=dist.ReduceOp.MAX)
-    stage_ms = dict(zip(("local_sort", "splitters", "merge_level_1", "merge_levels_local", "final_sort", "closing"), [round(float(x), 3) for x in st_t.tolist()]))
+    stage_ms = dict(zip(stage_names, [round(float(x), 3) for x in st_t.tolist()])) if native is not None else None
 
     # ---- the other four datasets at this size (range / inverted arrive already range-partitioned) ------------------
     per_dataset = {args.dataset: round(total / ms_max / 1e6, 2)}
@@ -535,7 +538,7 @@ def bench_distributed(args):
 
         def e2e_once():
             d_shard.copy_(h_in, non_blocking=True)
-            res = dsort.distributed_sort(d_shard, ops, dist, KEY_TYPE, scratch=scratch)
+            res = step(d_shard)
             h_out[:res.numel()].copy_(res, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return res.numel()
@@ -559,7 +562,7 @@ def bench_distributed(args):
     else:
         e2e = {"value": None, "unit": UNIT, "skipped": "not enough free host memory for the pinned shard buffers",
                "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    out = dsort.distributed_sort(shard, ops, dist, KEY_TYPE, scratch=scratch)
+    out = step()
     torch.cuda.synchronize()
 
     # global verification: locally sorted, boundaries ordered across ranks, multiset preserved, exact balance
@@ -569,22 +572,23 @@ def bench_distributed(args):
             raise RuntimeError("bench: distributed output failed verification")
         peak, peak_src = measured_hbm_peak()
         levels = max(1, (world - 1).bit_length())
-        merge_path = exchange == "p2p" and args.final == "merge" and (world & (world - 1)) == 0
+        merge_path = exchange == "native" or (exchange == "p2p" and args.final == "merge" and (world & (world - 1)) == 0)
         # algorithmic HBM bytes per key and GPU: the local sort (36) + the final step -- a merge tree reads and writes
         # every key once per level (8 B/key/level; level 1 reads over NVLink, writes locally), a final sort is 36 more
         # (the fused pull kernel replaces the histogram read by the NVLink read)
         sort_bpk = KEY_BYTES + PASSES * 2 * KEY_BYTES
         hbm_bpk = sort_bpk + (2 * KEY_BYTES * levels if merge_path else sort_bpk)
         nvlink_bytes = KEY_BYTES * n_local * (world - 1) / world
-        lvl1 = stage_ms.get("merge_level_1") or stage_ms.get("final_sort") or None
+        lvl1 = (stage_ms or {}).get("merge_level_1") or None
         line = {
             "metric": METRIC_DIST, "value": total / ms_max / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(world, args.dataset), "keys_total": total, "keys_per_gpu": n_local,
-                       "exchange": (("pairwise merge tree reading the peers' sorted runs over NVLink (CUDA IPC)" if args.final == "merge"
+                       "api": "rs_dist_create_rank / rs_dist_sort (C ABI; NCCL + CUDA IPC inside)" if exchange == "native" else "radix-sort_b200.dist (Python orchestration, A/B)",
+                       "exchange": (("pairwise merge tree reading the peers' sorted runs over NVLink (CUDA IPC)" if (args.final == "merge" or exchange == "native")
                                      else "fused peer-memory pull + histogram kernel (CUDA IPC over NVLink) + final onesweep passes")
-                                    if exchange == "p2p" else "NCCL all_to_all_single + final local sort"),
+                                    if exchange in ("p2p", "native") else "NCCL all_to_all_single + final local sort"),
                        "l2": "shards are GiBs, far larger than L2",
                        "datasets_gkeys_s": per_dataset,
                        "exact_parity": f"{parity_cases} reduced-size cases (4 key types x 5 datasets, 2^22 keys) equal to numpy on this box "
@@ -627,8 +631,9 @@ def main():
     ap.add_argument("--final", default="merge", choices=["merge", "sort"],
                     help="multi-GPU final local step with --exchange p2p: merge tree of the P received sorted runs (default) or a "
                          "full local onesweep sort fed by the fused pull + histogram kernel")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
-                    help="multi-GPU exchange: p2p = fused peer-memory pull + histogram kernel (default), nccl = all_to_all_single")
+    ap.add_argument("--exchange", default="native", choices=["native", "p2p", "nccl"],
+                    help="multi-GPU path: native = rs_dist_* behind the C ABI (default; merge tree over peer memory), p2p = the same "
+                         "exchange orchestrated from Python (A/B), nccl = all_to_all_single + final sort (A/B)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

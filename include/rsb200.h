@@ -128,8 +128,13 @@ int rs_device_count(int* n);
 int rs_context_create(int device, rs_context* out);
 int rs_context_destroy(rs_context ctx);
 int rs_context_sm_count(rs_context ctx, int* n);
-/* 1 if the device passed the self-test that allows ranking with one shared atomic per key (see rs_kernels.cuh);
- * sorters then use that mode unless RS_NO_ATOMIC_RANK is given (env RSB200_NO_ATOMIC_RANK=1 disables it globally). */
+/* 1 if sorters of this context rank with one shared-memory atomic per key (the fast default).  That mode is stable
+ * -- and every LSD pass must be -- only because the hardware serves the lanes of one warp instruction that hit the same
+ * shared word in ascending lane order.  NVIDIA does not document this, so it is not assumed: rs_context_create tests
+ * the property in isolation AND sorts 2^20 keys + index payload of heavily colliding digits through the production
+ * kernels, checking sortedness and the stable permutation on the device; any violation (a future driver or chip)
+ * leaves the context in the lane-bitmap mode, which relies only on the PTX memory model and is about a third slower.
+ * RS_NO_ATOMIC_RANK per sorter, or env RSB200_NO_ATOMIC_RANK=1 globally, select the bitmap mode by hand. */
 int rs_context_atomic_rank(rs_context ctx, int* enabled);
 int rs_stream_create(rs_context ctx, rs_stream* out);
 /* Wrap an existing cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); not owned. */
@@ -192,7 +197,7 @@ int rs_sorter_reset_runtimes(rs_sorter s);
 /* number of kernels launched by this sorter so far (for the bench's gpu_launches claim) */
 int rs_sorter_launch_count(rs_sorter s, uint64_t* out);
 
-/* ---- multi-GPU building blocks (one process per GPU; the collectives themselves are the caller's) ----------
+/* ---- multi-GPU building blocks (what rs_dist_* is made of; for callers that bring their own collectives) ----------
  * The reference has no counterpart (single OpenCL device, Common/ComputeState.cpp:10-12). */
 int rs_device_alloc(rs_context ctx, size_t bytes, void** out);      /* plain cudaMalloc: exportable through CUDA IPC */
 int rs_device_free(rs_context ctx, void* p);
@@ -221,6 +226,40 @@ int rs_sorter_sort_segments_device(rs_sorter s, rs_stream st, int num_segments, 
 int rs_merge_runs_device(rs_context ctx, rs_stream st, rs_key_type type, int num_jobs, const void* const* d_a_ptrs,
                          const uint64_t* a_counts, const void* const* d_b_ptrs, const uint64_t* b_counts,
                          void* const* d_out_ptrs, uint64_t* d_splits, uint64_t splits_capacity);
+
+/* ---- multi-GPU sort (BASELINE.json configs[4]) -------------------------------------------------------
+ * One NVSwitch box, keys only, 32- and 64-bit integer keys.  Every GPU sorts its shard (onesweep), exact splitters are
+ * found by refinement rounds on the devices (one ncclAllReduce per round, on the sort's stream), and the final local
+ * step is a merge tree whose first level reads the peers' sorted runs straight over NVLink (exchange and merge are
+ * one kernel).  Afterwards GPU r holds exactly floor((r+1)N/P) - floor(rN/P) keys, keys(r) <= keys(r+1), and the
+ * concatenation over the GPUs is the sorted input.  NCCL (libnccl.so.2) is loaded at run time; RSB200_NCCL_LIB
+ * overrides the path.  Asynchronous NCCL errors (ncclCommGetAsyncError) surface as RS_CALCULATION_FAILED.
+ * The reference has no counterpart (one OpenCL device, Common/ComputeState.cpp:10-12).
+ *
+ * Two ways to drive it:
+ *   rs_dist_create       one process drives all `ngpus` devices (peer access between them); rs_dist_sort takes and
+ *                        returns arrays of `ngpus` entries, in the order of `devices` (NULL = 0 .. ngpus-1)
+ *   rs_dist_create_rank  one process per GPU (rank of world): `id` comes from rs_dist_unique_id on one rank and is
+ *                        handed to the others by the caller (MPI, torch.distributed, a file ...); the buffers the peers
+ *                        read are exported through CUDA IPC; work runs on the caller's stream `st`; arrays have 1 entry */
+typedef struct rs_dist_s* rs_dist;
+#define RS_DIST_ID_BYTES 128
+#define RS_DIST_STAGES 6
+int rs_dist_unique_id(unsigned char id[RS_DIST_ID_BYTES]);
+int rs_dist_create(int ngpus, const int* devices, rs_key_type type, uint64_t max_keys_per_gpu, rs_dist* out);
+int rs_dist_create_rank(rs_context ctx, rs_stream st, rs_key_type type, uint64_t max_keys_per_gpu, int rank, int world,
+                        const unsigned char id[RS_DIST_ID_BYTES], rs_dist* out);
+int rs_dist_destroy(rs_dist d);
+int rs_dist_num_local(rs_dist d, int* n);   /* GPUs this handle drives: ngpus, or 1 */
+/* Sort the union of the shards (d_shards[i]: n_in[i] <= max_keys_per_gpu keys on local GPU i; the shards are not
+ * modified).  d_out[i] / n_out[i] receive local GPU i's slice of the global order: a pointer into buffers owned by the
+ * handle, valid until the next rs_dist_sort.  Synchronises the streams once in the middle (the cut table is read back);
+ * the tail of the work (merge tree, closing all-reduce) is only enqueued: rs_dist_sync, or the caller's stream. */
+int rs_dist_sort(rs_dist d, const void* const* d_shards, const uint64_t* n_in, void** d_out, uint64_t* n_out);
+int rs_dist_sync(rs_dist d);
+/* Device time (ms, CUDA events) of the stages of the last sort on local GPU `local_index`: [0] local sort,
+ * [1] splitters + cut table, [2] merge level 1 (NVLink), [3] local merge levels, [4] closing all-reduce, [5] total. Blocks. */
+int rs_dist_stage_ms(rs_dist d, int local_index, double out[RS_DIST_STAGES]);
 
 /* ---- device-side helpers used by the harness and the multi-GPU path ----------------------- */
 /* Fill d_out[0..n) with elements [global_offset, global_offset+n) of a dataset of total_n

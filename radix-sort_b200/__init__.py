@@ -14,5 +14,5 @@ There is no CPU fallback: loading fails loudly when ``librsb200.so`` is missing.
 from .capi import (  # noqa: F401
     KEY_TYPES, DATASET_KINDS, RS_WITH_PERMUTATION, RS_NO_TMA, RS_NO_PROFILE, RS_NO_KEY_BUFFERS, RS_NO_PASS_SKIP, RS_NO_ATOMIC_RANK, RS_NO_SMALL_PATH,
     RsError, Context, Stream, Sorter, HostBuffer, build_library, library_path, load_library,
-    declared_symbols, round_up_keys, status_string, key_dtype,
+    declared_symbols, round_up_keys, status_string, key_dtype, DistSorter, dist_unique_id, DIST_STAGES,
 )

@@ -114,6 +114,14 @@ def load_library():
         "rs_check_device": ([vp, vp, i, vp, u64, C.POINTER(u64 * 4)], i),
         "rs_check_permutation_device": ([vp, vp, i, vp, vp, vp, u64, C.POINTER(u64 * 2)], i),
         "rs_lower_bound_device": ([vp, vp, i, vp, u64, vp, u64, vp], i),
+        "rs_dist_unique_id": ([C.c_char_p], i),
+        "rs_dist_create": ([i, C.POINTER(i), i, u64, C.POINTER(vp)], i),
+        "rs_dist_create_rank": ([vp, vp, i, u64, i, i, C.c_char_p, C.POINTER(vp)], i),
+        "rs_dist_destroy": ([vp], i),
+        "rs_dist_num_local": ([vp, C.POINTER(i)], i),
+        "rs_dist_sort": ([vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)], i),
+        "rs_dist_sync": ([vp], i),
+        "rs_dist_stage_ms": ([vp, i, C.POINTER(C.c_double * 6)], i),
     }
     for name, (args, res) in sig.items():
         f = getattr(lib, name)
@@ -361,4 +369,62 @@ class Sorter:
     def close(self):
         if self.handle:
             self.lib.rs_sorter_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+DIST_STAGES = ("local_sort", "splitters", "merge_level_1", "merge_levels_local", "closing", "total")
+
+
+def dist_unique_id() -> bytes:
+    """ncclUniqueId for rs_dist_create_rank: create on one rank, hand the 128 bytes to the others."""
+    buf = C.create_string_buffer(128)
+    _check(load_library().rs_dist_unique_id(buf))
+    return buf.raw
+
+
+class DistSorter:
+    """Binding of rs_dist: the multi-GPU sort of one NVSwitch box behind the C ABI (NCCL + peer memory inside).
+    `DistSorter.rank(...)`: this process drives one GPU of `world`; `DistSorter.all_gpus(...)`: one process, all GPUs."""
+
+    def __init__(self, handle, key_type: str, n_local: int):
+        self.lib, self.handle, self.key_type, self.n_local_gpus = load_library(), handle, key_type, n_local
+
+    @classmethod
+    def rank(cls, ctx: Context, stream: Stream, key_type: str, max_keys_per_gpu: int, rank: int, world: int, unique_id: bytes):
+        h = C.c_void_p()
+        _check(ctx.lib.rs_dist_create_rank(ctx.handle, stream.handle, KEY_TYPES[key_type], max_keys_per_gpu, rank, world,
+                                           C.create_string_buffer(unique_id, 128), C.byref(h)))
+        return cls(h, key_type, 1)
+
+    @classmethod
+    def all_gpus(cls, key_type: str, max_keys_per_gpu: int, devices=None, ngpus=None):
+        lib = load_library()
+        n = len(devices) if devices is not None else ngpus
+        devs = (C.c_int * n)(*devices) if devices is not None else None
+        h = C.c_void_p()
+        _check(lib.rs_dist_create(n, devs, KEY_TYPES[key_type], max_keys_per_gpu, C.byref(h)))
+        return cls(h, key_type, n)
+
+    def sort(self, shard_ptrs, counts):
+        """shard_ptrs / counts: one entry per GPU this handle drives.  Returns [(device pointer, keys)] per GPU: this GPU's
+        slice of the global order, in buffers owned by the handle (valid until the next sort); the tail of the work is
+        stream-ordered (see rs_dist_sort)."""
+        k = self.n_local_gpus
+        ins = (C.c_void_p * k)(*[C.c_void_p(int(p)) if p else None for p in shard_ptrs])
+        ns = (C.c_uint64 * k)(*[int(c) for c in counts])
+        outs, n_out = (C.c_void_p * k)(), (C.c_uint64 * k)()
+        _check(self.lib.rs_dist_sort(self.handle, ins, ns, outs, n_out))
+        return [(outs[i] or 0, int(n_out[i])) for i in range(k)]
+
+    def sync(self):
+        _check(self.lib.rs_dist_sync(self.handle))
+
+    def stage_ms(self, local_index: int = 0) -> dict:
+        out = (C.c_double * 6)()
+        _check(self.lib.rs_dist_stage_ms(self.handle, local_index, C.byref(out)))
+        return dict(zip(DIST_STAGES, [float(x) for x in out]))
+
+    def close(self):
+        if self.handle:
+            self.lib.rs_dist_destroy(self.handle)
             self.handle = C.c_void_p()

@@ -431,9 +431,9 @@ struct OnesweepSmem {
     static constexpr size_t off_stage1  = off_stage0 + stage_bytes;
     static constexpr size_t off_vstage  = off_stage1 + stage_bytes;
     static constexpr size_t off_tab     = off_vstage + (HAS_VALS ? sizeof(uint32_t) * TILE : 0);
-    static constexpr size_t off_kptr    = off_tab + sizeof(uint32_t) * GROUPS * RADIX;
-    static constexpr size_t off_vptr    = off_kptr + sizeof(void*) * RADIX;
-    static constexpr size_t off_ptot    = off_vptr + (HAS_VALS ? sizeof(void*) * RADIX : 0);
+    static constexpr size_t off_koff    = off_tab + sizeof(uint32_t) * GROUPS * RADIX;   // run start - tile position, low word
+    static constexpr size_t off_khi     = off_koff + sizeof(uint32_t) * RADIX;           // high word (passes over > 2^32 keys)
+    static constexpr size_t off_ptot    = off_khi + sizeof(uint32_t) * RADIX;
     static constexpr size_t off_wsum    = off_ptot + sizeof(uint32_t) * PARTS * RADIX;
     static constexpr size_t off_mbar    = off_wsum + sizeof(uint32_t) * 16;
     static constexpr size_t off_tile    = off_mbar + sizeof(uint64_t) * 2;
@@ -482,8 +482,9 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
     KeyT* const        stage0  = reinterpret_cast<KeyT*>(smem_raw + L::off_stage0);  // stage s = stage0 + s*TILE
     uint32_t* const    vstage  = reinterpret_cast<uint32_t*>(smem_raw + L::off_vstage);
     uint32_t* const    tab     = reinterpret_cast<uint32_t*>(smem_raw + L::off_tab);   // [group][digit]
-    KeyT** const       kptr    = reinterpret_cast<KeyT**>(smem_raw + L::off_kptr);     // [digit] -> keys_out run - tile pos
-    uint32_t** const   vptr    = reinterpret_cast<uint32_t**>(smem_raw + L::off_vptr);
+    uint32_t* const    koff    = reinterpret_cast<uint32_t*>(smem_raw + L::off_koff);  // [digit] run start - tile pos (32-bit lookup)
+    uint32_t* const    khi     = reinterpret_cast<uint32_t*>(smem_raw + L::off_khi);
+    const bool         wide    = a.n > (1ull << 32);
     uint32_t* const    ptot    = reinterpret_cast<uint32_t*>(smem_raw + L::off_ptot);  // [part][digit] partial digit totals
     uint32_t* const    wsum    = reinterpret_cast<uint32_t*>(smem_raw + L::off_wsum);
     uint64_t* const    mbar    = reinterpret_cast<uint64_t*>(smem_raw + L::off_mbar);
@@ -701,10 +702,10 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
             // the last tile of a chunk hands the next chunk its base (its inclusive prefix = the chunk's counts)
             if ((t % a.tiles_per_chunk) == a.tiles_per_chunk - 1 && chunk + 1 < a.num_chunks)
                 st_base(cb_ptr + RADIX, BASE_READY | (cb + excl + count));
-            // run pointer minus the run's tile-local start: element at tile position p goes to kptr[d][p]
-            const long long run0 = static_cast<long long>(cb + excl) - static_cast<long long>(local_base);
-            kptr[sd] = a.keys_out + run0;
-            if constexpr (HAS_VALS) vptr[sd] = a.vals_out + run0;
+            // run start minus the run's tile-local start: the element at tile position p goes to out[run0 + p]
+            const unsigned long long run0 = cb + excl - local_base;  // may wrap below zero; run0 + p never does
+            koff[sd] = static_cast<uint32_t>(run0);
+            if (wide) khi[sd] = static_cast<uint32_t>(run0 >> 32);
         }
         __syncthreads();  // (D) staged tile + run pointers visible; nobody reads the tables any more
 
@@ -717,8 +718,10 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
             if (FULL || p < valid) {
                 const KeyT     k = stg[swz(p)];
                 const uint32_t d = digit_of<FK>(k, ds);
-                kptr[d][p]       = k;
-                if constexpr (HAS_VALS) vptr[d][p] = vstage[swz(p)];
+                uint64_t       o = static_cast<uint32_t>(koff[d] + p);
+                if (wide) o = ((static_cast<uint64_t>(khi[d]) << 32) | koff[d]) + p;
+                a.keys_out[o] = k;
+                if constexpr (HAS_VALS) a.vals_out[o] = vstage[swz(p)];
             }
         }
         __syncthreads();  // (E) stage free again; sh_tile[s^1] published

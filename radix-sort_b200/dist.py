@@ -1,5 +1,12 @@
 """Multi-GPU sort on one NVSwitch box: one process per GPU (torch.distributed), keys-only.
 
+The product path is `NativeDistSort` at the end of this file: a thin binding of rs_dist_* (include/rsb200.h) -- local
+sorts, splitter refinement on the devices, NCCL collectives, peer mapping and the merge tree all live behind the C ABI
+(csrc/rs_dist_api.inl); torch.distributed only hands the ncclUniqueId to the other ranks.  The rest of this file is the
+first, Python-orchestrated version of the same path.  It is kept because its host logic (`plan_exchange`) is what the
+gloo tests exercise on CPU and what the C++ planner is checked against (tests/test_dist_plan_cpu.py), and for A/B runs
+(`bench.py --exchange p2p|nccl`).
+
 Path (BASELINE.json north_star): every GPU sorts its shard with the local onesweep,
 MSD splitter histograms (11 bits per refinement round) are all-reduced, every rank computes the same exact
 splitters (ties on a splitter value are split by count -- equal keys are indistinguishable), key
@@ -32,6 +39,10 @@ class CudaOps:
 
     def __init__(self, rsb, ctx, stream, key_type: str, max_keys: int):
         import torch
+        # the collectives that order this rank's kernels against its peers run on torch's current stream: the kernels
+        # must run there too, or a peer could overwrite a shard that is still being read
+        if getattr(stream, "wrapped", None) != torch.cuda.current_stream().cuda_stream:
+            raise ValueError("CudaOps: `stream` must wrap torch's current CUDA stream")
         self.torch, self.rsb, self.ctx, self.stream, self.key_type = torch, rsb, ctx, stream, key_type
         self.tdt = torch.int32 if _key_bits(key_type) == 32 else torch.int64
         self.sorter = rsb.Sorter(ctx, key_type, max_keys, rsb.RS_NO_KEY_BUFFERS | rsb.RS_NO_PROFILE)
@@ -63,19 +74,6 @@ class CudaOps:
                              pos.data_ptr())
         self.stream.sync()
         return pos.cpu().numpy()
-
-    def lower_bound_device(self, sorted_keys, queries):
-        """Same search with the queries (key storage dtype) and the result (int64) staying on the device.  No host
-        synchronisation when self.stream wraps torch's current stream (as bench.py and the tools set it up)."""
-        pos = self.torch.empty(queries.numel(), dtype=self.torch.int64, device=queries.device)
-        same_stream = getattr(self.stream, "wrapped", None) == self.torch.cuda.current_stream().cuda_stream
-        if not same_stream:
-            self.torch.cuda.current_stream().synchronize()   # the queries were produced on torch's stream
-        self.ctx.lower_bound(self.stream, self.key_type, sorted_keys.data_ptr(), sorted_keys.numel(), queries.data_ptr(),
-                             queries.numel(), pos.data_ptr())
-        if not same_stream:
-            self.stream.sync()
-        return pos
 
     # ---- peer-memory exchange (NVLink, CUDA IPC) ---------------------------------------------------------
     def enable_p2p(self, dist, capacity_keys: int, group=None):
@@ -214,79 +212,6 @@ def plan_exchange(sorted_keys, ops, dist, key_type: str, group=None, device=None
     return cuts, t_recv.cpu().numpy()
 
 
-def plan_exchange_device(sorted_keys, ops, dist, key_type: str, group=None, device=None):
-    """plan_exchange with the refinement state kept on the device: same splitters, same cuts, no host round trip.
-
-    The host version pays a device->host->device round trip for every lower-bound query set and every all-reduce
-    (about ten per plan; 1.9 ms of the 25 ms step at 8 GPUs).  Here the queries of a round are built from the previous
-    round's result with a handful of tiny tensor ops, `ops.lower_bound_device` (rs_lower_bound_device) reads them where
-    they are, and the collectives run on the device tensors.  Returns the cuts as an int64 DEVICE tensor of world+1
-    entries; the caller reads it back together with whatever else it gathers (one synchronisation per sort).
-    Ordered-unsigned key values are carried as int64 bit patterns; 64-bit keys rely on two's complement wrap-around.
-    """
-    import torch
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    bits, sign = _key_bits(key_type), _sign(key_type)
-    n_local = int(sorted_keys.numel())
-    dev = device if device is not None else sorted_keys.device
-    i64 = dict(dtype=torch.int64, device=dev)
-    if world == 1:
-        return torch.tensor([0, n_local], **i64)
-    mask = (1 << bits) - 1 if bits < 64 else -1           # as an int64 scalar
-    sign64 = sign if sign < (1 << 63) else sign - (1 << 64)
-
-    def positions(ordered, top_flags):
-        """lower bound of ordered-unsigned values in the local shard; entries flagged in top_flags mean 2^bits"""
-        vals = (ordered & mask) ^ sign64                  # key bit patterns
-        if bits == 32:
-            vals = ((vals ^ 0x80000000) - 0x80000000).to(torch.int32)   # the low 32 bits as an int32 bit pattern
-        pos = ops.lower_bound_device(sorted_keys, vals.contiguous())
-        return torch.where(top_flags, torch.full_like(pos, n_local), pos)
-
-    w = world - 1
-    ranks = torch.arange(1, world, **i64)
-    prefix = torch.zeros(w, **i64)    # per splitter: ordered-unsigned key bits resolved so far
-    below = torch.zeros(w, **i64)     # per splitter: number of keys globally below `prefix`
-    targets = None
-    resolved, level = 0, 0
-    while resolved < bits:
-        width = min(LEVEL_BITS, bits - resolved)
-        fan = 1 << width
-        shift = bits - resolved - width
-        steps = torch.arange(fan + 1, **i64) << shift
-        bases = prefix[:1] * 0 if level == 0 else prefix           # level 0: one histogram serves every splitter
-        q = bases[:, None] + steps[None, :]                        # [len(bases), fan + 1]
-        # the last boundary of a row is base + fan << shift, a positive multiple of fan << shift: it is 2^bits itself
-        # exactly when its low `bits` bits are zero
-        top = torch.zeros_like(q, dtype=torch.bool)
-        top[:, -1] = (q[:, -1] & mask) == 0
-        pos = positions(q.reshape(-1), top.reshape(-1)).view(q.shape)
-        counts = (pos[:, 1:] - pos[:, :-1]).contiguous()
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)  # global sub-range counts
-        if level == 0:
-            targets = (ranks * counts[0].sum()) // world            # global rank of the first key of rank j
-            counts = counts.expand(w, fan)
-        cum = torch.cat((below[:, None], below[:, None] + torch.cumsum(counts, dim=1)), dim=1)   # [w, fan + 1]
-        b = (torch.searchsorted(cum, targets[:, None].contiguous(), right=True) - 1).clamp_(0, fan - 1)   # cum[b] <= target < cum[b+1]
-        prefix = prefix + (b[:, 0] << shift)
-        below = torch.gather(cum, 1, b)[:, 0]
-        resolved += width
-        level += 1
-    # prefix[j] is now an exact key value v_j; the copies of v_j are split by count, in rank order
-    pair = torch.stack((prefix, prefix + 1), dim=1)                # v and v + 1 (2^bits when v is the largest key)
-    top = torch.zeros_like(pair, dtype=torch.bool)
-    top[:, 1] = (pair[:, 1] & mask) == 0
-    pos = positions(pair.reshape(-1), top.reshape(-1)).view(w, 2)
-    lb, eq_local = pos[:, 0], pos[:, 1] - pos[:, 0]
-    parts = [torch.empty_like(eq_local) for _ in range(world)]
-    dist.all_gather(parts, eq_local.contiguous(), group=group)
-    before_me = torch.stack(parts)[:rank].sum(dim=0) if rank else torch.zeros_like(eq_local)
-    share = torch.minimum((targets - below - before_me).clamp_(min=0), eq_local)   # my copies that belong to ranks <= j
-    cuts = torch.cat((torch.zeros(1, **i64), lb + share, torch.full((1,), n_local, **i64)))
-    return torch.cummax(cuts, dim=0).values   # equal splitters (heavy duplicates) keep the cuts monotone
-
-
 def distributed_sort(keys, ops, dist, key_type: str, scratch=None, group=None):
     """Sort the union of all ranks' `keys`; returns this rank's slice of the global order (device tensor).
 
@@ -343,12 +268,8 @@ def _distributed_sort_p2p(keys, ops, dist, key_type: str, s, group):
     sorted_local = RawBuf(ops.p2p_local[sel], n_local, device=keys.device)
     mark("local sort")
     # 2. exact splitters (all-reduces inside: every peer's local sort is complete once they return)
-    if os.environ.get("RSB200_DEVICE_SPLITTERS") == "1":   # opt-in until it has been timed on the GPU box
-        cuts_dev = plan_exchange_device(sorted_local, ops, dist, key_type, group=group, device=keys.device)
-        mine = torch.cat((cuts_dev, torch.tensor([sel], dtype=torch.int64, device=keys.device)))
-    else:
-        cuts, _ = plan_exchange(sorted_local, ops, dist, key_type, group=group, device=keys.device, need_recv_counts=False)
-        mine = torch.from_numpy(np.concatenate((cuts, [sel])).astype(np.int64)).to(keys.device)
+    cuts, _ = plan_exchange(sorted_local, ops, dist, key_type, group=group, device=keys.device, need_recv_counts=False)
+    mine = torch.from_numpy(np.concatenate((cuts, [sel])).astype(np.int64)).to(keys.device)
     mark("splitters")
     # 3. everybody learns everybody's cut positions and buffer selector
     parts = [torch.empty_like(mine) for _ in range(world)]
@@ -421,3 +342,45 @@ def _merge_tree(ops, key_type, ptrs, counts, buf_x, buf_y, n_total, kb, scratch)
     dst = bufs[(level - 1) & 1]
     assert final_ptr == dst.data_ptr() and final_n == n_total
     return dst[:n_total]
+
+
+class _DevicePtr:
+    """A raw device range as a CUDA-array-interface object (torch.as_tensor wraps it without a copy)."""
+
+    def __init__(self, ptr: int, n: int, itemsize: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4" if itemsize == 4 else "<i8", "data": (ptr, False),
+                                         "version": 2}
+
+
+class NativeDistSort:
+    """One rank of the multi-GPU sort behind the C ABI (rs_dist_create_rank / rs_dist_sort).  `stream` must wrap the
+    CUDA stream the caller orders its own work on (torch's current stream in bench.py): the sort is enqueued there."""
+
+    def __init__(self, rsb, ctx, stream, key_type: str, max_keys_per_gpu: int, dist, group=None):
+        import torch
+        cur = torch.cuda.current_stream().cuda_stream
+        if getattr(stream, "wrapped", None) != cur:
+            raise ValueError("NativeDistSort: `stream` must wrap torch's current CUDA stream (rsb.Stream(ctx, "
+                             "torch.cuda.current_stream().cuda_stream)): results are consumed by torch on that stream")
+        self.torch, self.rsb, self.key_type = torch, rsb, key_type
+        self.kb = 4 if _key_bits(key_type) == 32 else 8
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if self.rank == 0:
+            ident.copy_(torch.frombuffer(bytearray(rsb.dist_unique_id()), dtype=torch.uint8))
+        dist.broadcast(ident, src=0, group=group)
+        self.sorter = rsb.DistSorter.rank(ctx, stream, key_type, max_keys_per_gpu, self.rank, self.world, bytes(ident.cpu().tolist()))
+
+    def sort(self, shard):
+        """Sort the union of all ranks' shards; returns this rank's slice of the global order as a tensor that views the
+        sorter's output buffer (valid until the next sort)."""
+        (ptr, n), = self.sorter.sort([shard.data_ptr()], [shard.numel()])
+        if n == 0:
+            return shard[:0]
+        return self.torch.as_tensor(_DevicePtr(ptr, n, self.kb), device=shard.device)
+
+    def stage_ms(self):
+        return self.sorter.stage_ms(0)
+
+    def close(self):
+        self.sorter.close()

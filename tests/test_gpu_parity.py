@@ -628,6 +628,33 @@ def test_sort_device_rejects_aliased_buffers(rsb, gpu):
     s.close()
 
 
+def test_dist_abi_single_gpu(rsb, gpu, oracle):
+    # rs_dist_* on a one-GPU "box": NCCL is loaded and initialised, the sort degenerates to the local onesweep.
+    # (2 .. 8 GPUs: tests/cpp/dist_runner and bench.py --gpus N run the exact compares on the multi-GPU boxes.)
+    torch = _torch()
+    for t in ("u32", "i64"):
+        data = oracle.dataset("uniform", t, 300_007, SEED)
+        d = rsb.DistSorter.all_gpus(t, len(data) + 1024, ngpus=1)
+        dev = _dev(data)
+        torch.cuda.synchronize()
+        (ptr, n), = d.sort([dev.data_ptr()], [len(data)])
+        d.sync()
+        assert n == len(data)
+        out = torch.as_tensor(importlib_dist()._DevicePtr(ptr, n, data.itemsize), device="cuda")
+        assert np.array_equal(_host(out, data.dtype), np.sort(data))
+        assert d.stage_ms(0)["local_sort"] > 0
+        d.close()
+    with pytest.raises(rsb.RsError):
+        rsb.DistSorter.all_gpus("f32", 1024, ngpus=1)     # integer keys of 4 or 8 bytes only
+    with pytest.raises(rsb.RsError):
+        rsb.DistSorter.all_gpus("u32", 1024, ngpus=64)
+
+
+def importlib_dist():
+    import importlib
+    return importlib.import_module("radix-sort_b200.dist")
+
+
 # ---- BASELINE.json configs[1..3] at FULL size, EXACT: inputs from the reference's own generators (mt19937 /
 #      uniform_int_distribution streams, oracle.dataset == src/Dataset.h:84-137), sorted through the reference-facing
 #      upload -> sort -> download calls and compared byte for byte with np.sort -- what CRadixSortTask::ValidateResults
@@ -729,6 +756,36 @@ def test_lookback_chunk_handover_exact(tmp_path):
                          env=env, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count(" OK ") == 24 and "FAIL" not in out.stdout, out.stdout[-2000:]
+
+
+def test_pipelined_pass_variant_exact():
+    # RSB200_SWEEP_V2=1 selects the software-pipelined variant of the pass kernel (csrc/rs_sweep.cuh, an opt-in kept for
+    # the record of the round-2 experiments): every key type / payload / size class of tools/sanitize_driver.py, exact
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RSB200_SWEEP_V2="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize_driver.py"), "log2n=20"], capture_output=True,
+                         text=True, env=env, timeout=900)
+    assert out.returncode == 0 and "sanitize_driver PASSED" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
+    env["RSB200_DEBUG_TILES_PER_CHUNK"] = "3"     # and its chunk hand-over
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "debug_chunks.py")], capture_output=True, text=True,
+                         env=env, timeout=600)
+    assert out.returncode == 0 and out.stdout.count(" OK ") == 24 and "FAIL" not in out.stdout, out.stdout[-2000:]
+
+
+def test_merge_walk_order_regions_exact():
+    # RSB200_MERGE_ORDER_REGIONS=1: the region-strided walk order of the merge CTAs (csrc/rs_merge_order.h), the second
+    # instantiation of the merge tile kernel -- merge tree and merge levels of tools/sanitize_driver.py, exact
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RSB200_MERGE_ORDER_REGIONS="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize_driver.py"), "log2n=21"], capture_output=True,
+                         text=True, env=env, timeout=900)
+    assert out.returncode == 0 and "sanitize_driver PASSED" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
 
 
 def test_more_than_one_lookback_chunk(rsb, gpu):

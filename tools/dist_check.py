@@ -4,7 +4,7 @@ dataset and key type (4 x 5), plus exact balance of the output shards.  Used two
     multi-GPU bench line covers exact parity on that box;
   * stand-alone under torchrun:
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/dist_check.py [log2n_total=22]
-      [exchange=p2p|nccl] [final=merge|sort]"""
+      [exchange=native|p2p|nccl] [final=merge|sort]"""
 import importlib
 import os
 import sys
@@ -13,13 +13,16 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
 
 
-def run_checks(rsb, dsort, dist, torch, ctx, st, total, mode="p2p", final="merge", log=None):
+def run_checks(rsb, dsort, dist, torch, ctx, st, total, mode="native", final="merge", log=None):
     """Returns (cases, failures); every rank takes part (collectives inside)."""
     rank, world = dist.get_rank(), dist.get_world_size()
     failures, cases = 0, 0
     for key_type in ("u32", "i32", "u64", "i64"):
         np_dt = rsb.key_dtype(key_type)
         n_local = total // world + (17 * rank if key_type == "i32" else 0)  # ragged shards for one type
+        native = None
+        if mode == "native":   # the product path: rs_dist_* behind the C ABI
+            native = dsort.NativeDistSort(rsb, ctx, st, key_type, 2 * n_local + 4096, dist)
         ops = dsort.CudaOps(rsb, ctx, st, key_type, 2 * n_local + 4096)
         ops.final_step = final
         if mode == "p2p":
@@ -28,7 +31,7 @@ def run_checks(rsb, dsort, dist, torch, ctx, st, total, mode="p2p", final="merge
             shard = ops.empty(n_local)
             ctx.fill_dataset(st, key_type, kind, shard.data_ptr(), n_local, seed=0x5EED, global_offset=rank * (total // world),
                              total_n=total)
-            out = dsort.distributed_sort(shard, ops, dist, key_type)
+            out = native.sort(shard) if native is not None else dsort.distributed_sort(shard, ops, dist, key_type)
             torch.cuda.synchronize()
             sizes = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(world)]
             dist.all_gather(sizes, torch.tensor([n_local, out.numel()], dtype=torch.int64, device="cuda"))
@@ -52,6 +55,8 @@ def run_checks(rsb, dsort, dist, torch, ctx, st, total, mode="p2p", final="merge
                         f"sizes={sizes[:, 1].tolist()}")
                 failures += int(not (ok and bal))
         ops.close()
+        if native is not None:
+            native.close()
     f = torch.tensor([failures], dtype=torch.int64, device="cuda")
     dist.broadcast(f, src=0)
     return cases, int(f.item())
@@ -70,7 +75,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = rsb.Context(local_rank)
     st = rsb.Stream(ctx, torch.cuda.current_stream().cuda_stream)
-    _, failures = run_checks(rsb, dsort, dist, torch, ctx, st, total, args.get("exchange", "p2p"), args.get("final", "merge"),
+    _, failures = run_checks(rsb, dsort, dist, torch, ctx, st, total, args.get("exchange", "native"), args.get("final", "merge"),
                              log=lambda m: print(m, flush=True))
     dist.barrier()
     dist.destroy_process_group()

@@ -3,7 +3,7 @@
 # `--set full` capture of the two top kernels.  Outputs land in gpurun_out/ (summarised into profiles/ by
 # tools/summarize_profiles.py back in the build container).   usage: tools/gpu_profile.sh <tag>
 TAG=${1:-r1}
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu --no-other"
 mkdir -p gpurun_out
 $CMD > gpurun_out/${TAG}_bench_plain.json 2> gpurun_out/${TAG}_bench_plain.err || { echo "plain bench failed"; tail -5 gpurun_out/${TAG}_bench_plain.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
