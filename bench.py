@@ -345,7 +345,7 @@ def bench_single(args):
             traffic = json.load(f).get("onesweep_u32_keys_2^28_dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "rs_sweep_kernel<u32, keys-only> (one onesweep pass)", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": "rs_onesweep_kernel<u32, keys-only> (one pass)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": pass_ms,
                 "whole_sort": {"algorithmic_bytes": (KEY_BYTES + PASSES * 2 * KEY_BYTES) * n,
@@ -398,6 +398,8 @@ def bench_distributed(args):
     if exchange == "native":
         # the product path: rs_dist_create_rank / rs_dist_sort (C ABI): NCCL, peer mapping, splitters and merge tree inside
         native = dsort.NativeDistSort(rsb, ctx, st, KEY_TYPE, n_local + 1024, dist)
+    if native is None and os.environ.get("RSB200_DBG_EXTRA_COMM"):   # developer probe: an idle rs_dist handle next to the Python path
+        _idle = dsort.NativeDistSort(rsb, ctx, st, KEY_TYPE, 1 << 20, dist)
     ops = dsort.CudaOps(rsb, ctx, st, KEY_TYPE, (n_local + n_local // 8 + (1 << 20)) if native is None else 1024)
     ops.final_step = args.final   # "merge": pairwise merge tree over peer memory, "sort": fused pull + histogram + onesweep passes
     if exchange == "p2p":

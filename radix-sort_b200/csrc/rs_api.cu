@@ -258,7 +258,14 @@ static cudaError_t launch_hist_n(int grid, cudaStream_t st, const KeyT* keys, ui
             if (e != cudaSuccess) return e;
             configured |= bit;
         }
-        kern<<<grid, HIST_THREADS, HistCfg<NPASS>::bytes, st>>>(keys, n, hist, pt);
+        // whole bytes from bit 0 up: the kernel's fast digit extraction applies (see rs_histogram_kernel)
+        bool bytes = true;
+        KeyT key_flip = 0;
+        for (int p = 0; p < NPASS; ++p) {
+            bytes = bytes && pt.d[p].shift == 8 * p && pt.d[p].mask == 0xffu;
+            key_flip = static_cast<KeyT>(key_flip | (static_cast<KeyT>(pt.d[p].flip) << pt.d[p].shift));
+        }
+        kern<<<grid, HIST_THREADS, HistCfg<NPASS>::bytes, st>>>(keys, n, hist, pt, bytes ? 1 : 0, key_flip);
         return cudaGetLastError();
     }
 }

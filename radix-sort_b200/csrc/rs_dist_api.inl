@@ -132,9 +132,13 @@ int dist_alloc_rank(rs_dist d, DistRank& R) {
     const size_t kb    = d->ki.bytes;
     const size_t slack = 32 * static_cast<size_t>(d->world) + 64;   // intermediate runs of the merge tree start on 128-byte lines
     const int    W     = d->world;
+    // Sizes are rounded to whole 2 MiB pages: a peer mapping of an allocation that ends in a partial large page was
+    // measured to make the merge-path partition (random 32-byte probes over NVLink) 2x slower -- 5.3 instead of 2.6 ms at
+    // 2 GPUs, 2.9 instead of 1.1 ms at 8 -- while streaming reads did not care (profiles/README.md, round 2).
+    auto whole_pages = [](size_t bytes) { return (bytes + (size_t{2} << 20) - 1) & ~((size_t{2} << 20) - 1); };
     for (int i = 0; i < 2; ++i) {
-        RS_CUDA(cudaMalloc(&R.pair[i], std::max<size_t>(d->cap, 1) * kb + 256), RS_INITIALIZATION_FAILED);
-        RS_CUDA(cudaMalloc(&R.merge_buf[i], (d->cap + slack) * kb + 256), RS_INITIALIZATION_FAILED);
+        RS_CUDA(cudaMalloc(&R.pair[i], whole_pages(std::max<size_t>(d->cap, 1) * kb + 256)), RS_INITIALIZATION_FAILED);
+        RS_CUDA(cudaMalloc(&R.merge_buf[i], whole_pages((d->cap + slack) * kb + 256)), RS_INITIALIZATION_FAILED);
     }
     R.splits_cap = (d->cap + slack) / 1024 + 4ull * W + 64;
     RS_CUDA(cudaMalloc(reinterpret_cast<void**>(&R.splits), R.splits_cap * sizeof(uint64_t)), RS_INITIALIZATION_FAILED);

@@ -22,6 +22,23 @@
 #include <type_traits>
 #include <cuda_runtime.h>
 
+// Bounds checks of our own (compute-sanitizer is not available on the GPU pool this was developed on): a build with
+// -DRS_DEBUG_CHECKS traps on any out-of-range tile position, output index or look-back sum; tools/debug_checks.sh runs
+// the parity workloads against that build (profiles/r2_debug_checks.txt).
+#ifdef RS_DEBUG_CHECKS
+#include <cstdio>
+#define RS_DCHECK(cond)                                                                                   \
+    do {                                                                                                  \
+        if (!(cond)) {                                                                                    \
+            printf("RS_DCHECK failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__,      \
+                   static_cast<int>(blockIdx.x), static_cast<int>(threadIdx.x));                          \
+            __trap();                                                                                     \
+        }                                                                                                 \
+    } while (0)
+#else
+#define RS_DCHECK(cond) ((void)0)
+#endif
+
 namespace rsb {
 
 constexpr int      RADIX_BITS        = 8;
@@ -176,7 +193,7 @@ struct HistCfg {
 template <typename KeyT, int NPASS, bool FK>
 __global__ void __launch_bounds__(HIST_THREADS, 1)
 rs_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ hist /* [NPASS][256] */,
-                    PassTable pt) {
+                    PassTable pt, int byte_digits, KeyT key_flip) {
     constexpr int KV   = 16 / sizeof(KeyT);
     constexpr int COLS = HistCfg<NPASS>::COLS;
     extern __shared__ __align__(16) uint32_t hist_sh[];  // [NPASS][256][COLS]
@@ -190,10 +207,27 @@ rs_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long lon
     const uint64_t nvec = aligned ? n / KV : 0;
     const uint4*   cv   = reinterpret_cast<const uint4*>(keys);
 
+    // byte_digits (the usual whole-key sort: digit p is byte p of the key, key_flip = the sign bit of signed keys): the
+    // key is put into unsigned order ONCE, and the byte offset of a counter -- digit * COLS * 4 + col * 4 -- costs one
+    // shift and one LOP3 per digit (the generic path spends ~4.4 ALU instructions per atomic and was issue-bound: 71 % of
+    // the issue slots, profiles/r1d_ncu_full_summary.txt).
+    const uint32_t col_bits = col << 2;
     auto count_key = [&](KeyT k) {
+        if (byte_digits) {
+            constexpr int LG = COLS == 32 ? 7 : 6;   // log2 of the bytes per digit row
+            if constexpr (FK) k = float_order_bits(k, pt.d[0].finf); else k ^= key_flip;
 #pragma unroll
-        for (int p = 0; p < NPASS; ++p)
-            atomicAdd(&hist_sh[(p * RADIX + digit_of<FK>(k, pt.d[p])) * COLS + col], 1u);
+            for (int p = 0; p < NPASS; ++p) {
+                uint32_t off;
+                if (8 * p >= LG) off = static_cast<uint32_t>(k >> (8 * p - LG)); else off = static_cast<uint32_t>(k) << (LG - 8 * p);
+                off = (off & (0xffu << LG)) | col_bits;
+                atomicAdd(reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(hist_sh) + p * RADIX * COLS * sizeof(uint32_t) + off), 1u);
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < NPASS; ++p)
+                atomicAdd(&hist_sh[(p * RADIX + digit_of<FK>(k, pt.d[p])) * COLS + col], 1u);
+        }
     };
 
     // a block never counts more than 2^32 keys per column (the launcher keeps blocks below 2^31 keys)
@@ -431,9 +465,9 @@ struct OnesweepSmem {
     static constexpr size_t off_stage1  = off_stage0 + stage_bytes;
     static constexpr size_t off_vstage  = off_stage1 + stage_bytes;
     static constexpr size_t off_tab     = off_vstage + (HAS_VALS ? sizeof(uint32_t) * TILE : 0);
-    static constexpr size_t off_koff    = off_tab + sizeof(uint32_t) * GROUPS * RADIX;   // run start - tile position, low word
-    static constexpr size_t off_khi     = off_koff + sizeof(uint32_t) * RADIX;           // high word (passes over > 2^32 keys)
-    static constexpr size_t off_ptot    = off_khi + sizeof(uint32_t) * RADIX;
+    static constexpr size_t off_kptr    = off_tab + sizeof(uint32_t) * GROUPS * RADIX;
+    static constexpr size_t off_vptr    = off_kptr + sizeof(void*) * RADIX;
+    static constexpr size_t off_ptot    = off_vptr + (HAS_VALS ? sizeof(void*) * RADIX : 0);
     static constexpr size_t off_wsum    = off_ptot + sizeof(uint32_t) * PARTS * RADIX;
     static constexpr size_t off_mbar    = off_wsum + sizeof(uint32_t) * 16;
     static constexpr size_t off_tile    = off_mbar + sizeof(uint64_t) * 2;
@@ -482,9 +516,11 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
     KeyT* const        stage0  = reinterpret_cast<KeyT*>(smem_raw + L::off_stage0);  // stage s = stage0 + s*TILE
     uint32_t* const    vstage  = reinterpret_cast<uint32_t*>(smem_raw + L::off_vstage);
     uint32_t* const    tab     = reinterpret_cast<uint32_t*>(smem_raw + L::off_tab);   // [group][digit]
-    uint32_t* const    koff    = reinterpret_cast<uint32_t*>(smem_raw + L::off_koff);  // [digit] run start - tile pos (32-bit lookup)
-    uint32_t* const    khi     = reinterpret_cast<uint32_t*>(smem_raw + L::off_khi);
-    const bool         wide    = a.n > (1ull << 32);
+    // [digit] -> run pointer minus the run's tile-local start.  (32-bit element offsets instead of pointers were tried in
+    // round 2: the lookup is one wavefront cheaper, the address arithmetic and the >2^32-key branch cost more -- 0.679 ->
+    // 0.724 ms per pass, profiles/README.md.)
+    KeyT** const       kptr    = reinterpret_cast<KeyT**>(smem_raw + L::off_kptr);
+    uint32_t** const   vptr    = reinterpret_cast<uint32_t**>(smem_raw + L::off_vptr);
     uint32_t* const    ptot    = reinterpret_cast<uint32_t*>(smem_raw + L::off_ptot);  // [part][digit] partial digit totals
     uint32_t* const    wsum    = reinterpret_cast<uint32_t*>(smem_raw + L::off_wsum);
     uint64_t* const    mbar    = reinterpret_cast<uint64_t*>(smem_raw + L::off_mbar);
@@ -664,6 +700,7 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
             } else {
                 pos = (gt[d] >> CSHIFT) + ((r & 1) ? (rk[r >> 1] >> 16) : (rk[r >> 1] & 0xffffu));
             }
+            RS_DCHECK(pos < static_cast<uint32_t>(TILE));
             stg[swz(pos)] = key[r];
             if constexpr (HAS_VALS) vstage[swz(pos)] = val[r];
         }
@@ -692,6 +729,7 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
                         if (f == 2) done = true;
                     }
                 }
+                RS_DCHECK(excl + count <= CHUNK_MAX_KEYS);
                 st_status(my_status, STATUS_INCLUSIVE | static_cast<uint32_t>(excl + count));
             }
             // global offset of this chunk's first key with this digit (ready at once for chunk 0)
@@ -702,10 +740,10 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
             // the last tile of a chunk hands the next chunk its base (its inclusive prefix = the chunk's counts)
             if ((t % a.tiles_per_chunk) == a.tiles_per_chunk - 1 && chunk + 1 < a.num_chunks)
                 st_base(cb_ptr + RADIX, BASE_READY | (cb + excl + count));
-            // run start minus the run's tile-local start: the element at tile position p goes to out[run0 + p]
-            const unsigned long long run0 = cb + excl - local_base;  // may wrap below zero; run0 + p never does
-            koff[sd] = static_cast<uint32_t>(run0);
-            if (wide) khi[sd] = static_cast<uint32_t>(run0 >> 32);
+            // run pointer minus the run's tile-local start: element at tile position p goes to kptr[d][p]
+            const long long run0 = static_cast<long long>(cb + excl) - static_cast<long long>(local_base);
+            kptr[sd] = a.keys_out + run0;
+            if constexpr (HAS_VALS) vptr[sd] = a.vals_out + run0;
         }
         __syncthreads();  // (D) staged tile + run pointers visible; nobody reads the tables any more
 
@@ -718,10 +756,9 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
             if (FULL || p < valid) {
                 const KeyT     k = stg[swz(p)];
                 const uint32_t d = digit_of<FK>(k, ds);
-                uint64_t       o = static_cast<uint32_t>(koff[d] + p);
-                if (wide) o = ((static_cast<uint64_t>(khi[d]) << 32) | koff[d]) + p;
-                a.keys_out[o] = k;
-                if constexpr (HAS_VALS) a.vals_out[o] = vstage[swz(p)];
+                RS_DCHECK(kptr[d] + p >= a.keys_out && kptr[d] + p < a.keys_out + a.n);
+                kptr[d][p]       = k;
+                if constexpr (HAS_VALS) vptr[d][p] = vstage[swz(p)];
             }
         }
         __syncthreads();  // (E) stage free again; sh_tile[s^1] published
@@ -857,6 +894,7 @@ rs_small_sort_kernel(const KeyT* in, KeyT* out, const uint32_t* vin, uint32_t* v
             } else {
                 pos = atoms_add_return(&gt[d], 1u);  // same-word lanes are served in lane order (self-tested)
             }
+            RS_DCHECK(pos < static_cast<uint32_t>(SMALL_CAP));
             kbuf[(cur ^ 1) * SMALL_CAP + pos] = key[r];
             if constexpr (HAS_VALS) vbuf[(cur ^ 1) * SMALL_CAP + pos] = val[r];
         }

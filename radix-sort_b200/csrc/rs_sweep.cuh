@@ -27,8 +27,6 @@
 //   * two count/position tables (tile parity), 16-bit counters, two warps per 32-bit word ({warp 2j : low,
 //     warp 2j+1 : high}): half the words to scan and re-zero, 2 x 8 KB; the price is that the count atomic of the
 //     odd warps adds 65536 and cannot be the lane-merging ATOMS.POPC.INC (+0.4 wavefronts per 32 keys);
-//   * per-digit run pointers are 32-bit element offsets (a second word with the high half only when the pass moves
-//     more than 2^32 keys): the data-dependent lookup of the output loop is a 32-bit load;
 //
 // Stability rests on the same hardware property as before: lanes of ONE warp instruction that hit the same shared
 // word are served in ascending lane order (self-tested per context, see rs_api.cu); two warps that share a word
@@ -39,6 +37,13 @@
 #include "rs_kernels.cuh"
 
 namespace rsb {
+
+// How the output loop finds a digit's run: 2 = 64-bit run pointers (keys and values), 0 = 32-bit element offsets plus a
+// high word for passes over more than 2^32 keys.
+#ifndef RS_SWEEP_RUNPTR
+#define RS_SWEEP_RUNPTR 2
+#endif
+constexpr int SWEEP_RUNPTR = RS_SWEEP_RUNPTR;
 
 template <typename KeyT, bool HAS_VALS, int THREADS, int KPT>
 struct SweepSmem {
@@ -53,7 +58,8 @@ struct SweepSmem {
     static constexpr size_t off_tab     = off_vstage + (HAS_VALS ? sizeof(uint32_t) * TILE : 0);   // [2][GW][256]
     static constexpr size_t off_koff    = off_tab + sizeof(uint32_t) * 2 * GW * RADIX;
     static constexpr size_t off_khi     = off_koff + sizeof(uint32_t) * RADIX;
-    static constexpr size_t off_meta    = off_khi + sizeof(uint32_t) * RADIX;                       // [2][256]
+    static constexpr size_t off_vptr    = off_khi + sizeof(uint32_t) * RADIX;                       // value run pointers (RUNPTR 2)
+    static constexpr size_t off_meta    = off_vptr + ((SWEEP_RUNPTR == 2 && HAS_VALS) ? sizeof(void*) * RADIX : 0);   // [2][256]
     static constexpr size_t off_wsum    = off_meta + sizeof(uint32_t) * 2 * RADIX;
     static constexpr size_t off_mbar    = off_wsum + sizeof(uint32_t) * 16;
     static constexpr size_t off_tile    = off_mbar + sizeof(uint64_t) * 2;
@@ -101,6 +107,8 @@ rs_sweep_kernel(const OnesweepArgs<KeyT> a) {
     uint32_t* const    tab     = reinterpret_cast<uint32_t*>(smem_raw + L::off_tab);   // [slot][warp pair][digit], 2 x 16 bit
     uint32_t* const    koff    = reinterpret_cast<uint32_t*>(smem_raw + L::off_koff);  // [digit] run start - tile pos (low)
     uint32_t* const    khi     = reinterpret_cast<uint32_t*>(smem_raw + L::off_khi);   // high half, only if a.n > 2^32
+    KeyT** const       kptr    = reinterpret_cast<KeyT**>(smem_raw + L::off_koff);     // RUNPTR 2: [digit] run pointer - tile pos
+    uint32_t** const   vptr    = reinterpret_cast<uint32_t**>(smem_raw + L::off_vptr);
     uint32_t* const    meta    = reinterpret_cast<uint32_t*>(smem_raw + L::off_meta);  // [slot][digit] count | local_base << 16
     uint32_t* const    wsum    = reinterpret_cast<uint32_t*>(smem_raw + L::off_wsum);
     uint64_t* const    mbar    = reinterpret_cast<uint64_t*>(smem_raw + L::off_mbar);
@@ -273,13 +281,19 @@ rs_sweep_kernel(const OnesweepArgs<KeyT> a) {
         const uint32_t m = meta[s * RADIX + sd];
         const uint32_t cnt = m & 0xffffu, lbase = m >> 16;
         // publish the inclusive prefix, hand the next chunk its base, set the run offset of digit sd
+        RS_DCHECK(static_cast<unsigned long long>(excl) + cnt <= CHUNK_MAX_KEYS);
         if (in_chunk != 0) st_status(my_status, STATUS_INCLUSIVE | (excl + cnt));
         if (in_chunk == a.tiles_per_chunk - 1 && chunk + 1 < a.num_chunks)
             st_base(cb_ptr + RADIX, BASE_READY | (cb + excl + cnt));
         // run start minus the run's tile-local start: the element at tile position p goes to out[run0 + p]
         const unsigned long long run0 = cb + excl - lbase;  // may wrap below zero; run0 + p never does
-        koff[sd] = static_cast<uint32_t>(run0);
-        if (wide) khi[sd] = static_cast<uint32_t>(run0 >> 32);
+        if constexpr (SWEEP_RUNPTR == 2) {
+            kptr[sd] = a.keys_out + static_cast<long long>(run0);
+            if constexpr (HAS_VALS) vptr[sd] = a.vals_out + static_cast<long long>(run0);
+        } else {
+            koff[sd] = static_cast<uint32_t>(run0);
+            if (SWEEP_RUNPTR == 0 && wide) khi[sd] = static_cast<uint32_t>(run0 >> 32);
+        }
     };
 
     // ---- scatter of the tile in registers into its stage, in ranked order -------------------------------------
@@ -302,6 +316,7 @@ rs_sweep_kernel(const OnesweepArgs<KeyT> a) {
             } else {
                 pos = __byte_perm(atoms_add_return(&gt[d], one), 0u, hsel);
             }
+            RS_DCHECK(pos < static_cast<uint32_t>(TILE));
             stg[swz(pos)] = key[r];
             if constexpr (HAS_VALS) vstage[swz(pos)] = val[r];
         }
@@ -320,10 +335,16 @@ rs_sweep_kernel(const OnesweepArgs<KeyT> a) {
             if (FULL || p < valid) {
                 const KeyT     k = stg[swz(p)];
                 const uint32_t d = digit_of<FK>(k, ds);
-                uint64_t       o = static_cast<uint32_t>(koff[d] + p);
-                if (wide) o = ((static_cast<uint64_t>(khi[d]) << 32) | koff[d]) + p;
-                a.keys_out[o] = k;
-                if constexpr (HAS_VALS) a.vals_out[o] = vstage[swz(p)];
+                if constexpr (SWEEP_RUNPTR == 2) {
+                    RS_DCHECK(kptr[d] + p >= a.keys_out && kptr[d] + p < a.keys_out + a.n);
+                    kptr[d][p] = k;
+                    if constexpr (HAS_VALS) vptr[d][p] = vstage[swz(p)];
+                } else {
+                    uint64_t o = static_cast<uint32_t>(koff[d] + p);
+                    if (SWEEP_RUNPTR == 0 && wide) o = ((static_cast<uint64_t>(khi[d]) << 32) | koff[d]) + p;
+                    a.keys_out[o] = k;
+                    if constexpr (HAS_VALS) a.vals_out[o] = vstage[swz(p)];
+                }
             }
         }
     };
