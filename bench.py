@@ -398,8 +398,6 @@ def bench_distributed(args):
     if exchange == "native":
         # the product path: rs_dist_create_rank / rs_dist_sort (C ABI): NCCL, peer mapping, splitters and merge tree inside
         native = dsort.NativeDistSort(rsb, ctx, st, KEY_TYPE, n_local + 1024, dist)
-    if native is None and os.environ.get("RSB200_DBG_EXTRA_COMM"):   # developer probe: an idle rs_dist handle next to the Python path
-        _idle = dsort.NativeDistSort(rsb, ctx, st, KEY_TYPE, 1 << 20, dist)
     ops = dsort.CudaOps(rsb, ctx, st, KEY_TYPE, (n_local + n_local // 8 + (1 << 20)) if native is None else 1024)
     ops.final_step = args.final   # "merge": pairwise merge tree over peer memory, "sort": fused pull + histogram + onesweep passes
     if exchange == "p2p":

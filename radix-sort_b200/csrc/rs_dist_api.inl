@@ -132,9 +132,10 @@ int dist_alloc_rank(rs_dist d, DistRank& R) {
     const size_t kb    = d->ki.bytes;
     const size_t slack = 32 * static_cast<size_t>(d->world) + 64;   // intermediate runs of the merge tree start on 128-byte lines
     const int    W     = d->world;
-    // Sizes are rounded to whole 2 MiB pages: a peer mapping of an allocation that ends in a partial large page was
-    // measured to make the merge-path partition (random 32-byte probes over NVLink) 2x slower -- 5.3 instead of 2.6 ms at
-    // 2 GPUs, 2.9 instead of 1.1 ms at 8 -- while streaming reads did not care (profiles/README.md, round 2).
+    // Sizes are rounded to whole 2 MiB pages.  With allocations of cap * 4 + 256 bytes (a partial last large page) the
+    // merge-path partition kernel -- random 32-byte probes of a peer's shard over NVLink -- took 5.32 ms at 2 GPUs; with
+    // rounded sizes 2.66 ms, same kernel, same inputs (8 GPUs: 2.86 -> see profiles/README.md).  Streaming reads of the
+    // same mappings did not care.  Presumably the peer mapping falls back to small pages and the probes miss the TLB.
     auto whole_pages = [](size_t bytes) { return (bytes + (size_t{2} << 20) - 1) & ~((size_t{2} << 20) - 1); };
     for (int i = 0; i < 2; ++i) {
         RS_CUDA(cudaMalloc(&R.pair[i], whole_pages(std::max<size_t>(d->cap, 1) * kb + 256)), RS_INITIALIZATION_FAILED);
