@@ -8,6 +8,10 @@
 #include "../../include/rsb200.h"
 #include "rs_kernels.cuh"
 #include "rs_sweep.cuh"
+#ifdef RS_EXPERIMENTAL_PASSES   // round-2 experiments kept for the record (profiles/README.md); not part of the default build
+#include "rs_pass3.cuh"
+#include "rs_pass4.cuh"
+#endif
 #include "rs_merge.cuh"
 
 #include <algorithm>
@@ -348,6 +352,9 @@ static cudaError_t configure_pass(Kern kern, int device, int threads, size_t sme
     return cudaSuccess;
 }
 
+#ifndef RS_DEFAULT_PASS_GEN
+#define RS_DEFAULT_PASS_GEN 1
+#endif
 template <typename KeyT, bool HAS_VALS, bool ATOMIC, bool FK>
 static cudaError_t launch_pass_mode(rs_context ctx, cudaStream_t st, const OnesweepArgs<KeyT>& args) {
     using C = TileCfg<KeyT, HAS_VALS, ATOMIC>;
@@ -356,7 +363,32 @@ static cudaError_t launch_pass_mode(rs_context ctx, cudaStream_t st, const Onesw
         // RSB200_SWEEP_V2=1: the software-pipelined variant of the pass (rs_sweep.cuh; same tile shape and scratch layout).
         // Measured equal on 4-byte keys and slower on 8-byte keys and with the index payload (profiles/README.md), so
         // the first-generation kernel stays the default; the variant is kept runnable for that record.
-        static const bool sweep_v2 = std::getenv("RSB200_SWEEP_V2") != nullptr;
+        // RSB200_PASS=3: the third generation (rs_pass3.cuh: register prefetch instead of the TMA stage, exchange-and-clear
+        // table scan, 32-bit run starts).
+        static const int pass_gen = [] { const char* e = std::getenv("RSB200_PASS"); return e ? std::atoi(e) : RS_DEFAULT_PASS_GEN; }();
+#ifdef RS_EXPERIMENTAL_PASSES
+        if (pass_gen == 3) {
+            using L = Pass3Smem<KeyT, HAS_VALS, C::THREADS, C::KPT>;
+            auto kern = rs_pass3_kernel<KeyT, HAS_VALS, C::THREADS, C::KPT, C::MINB, FK>;
+            static thread_local PassLaunchState state;
+            cudaError_t e = configure_pass(kern, ctx->device, C::THREADS, L::total, state, &blocks_per_sm);
+            if (e != cudaSuccess) return e;
+            const uint64_t resident = static_cast<uint64_t>(blocks_per_sm) * ctx->sm_count;
+            kern<<<static_cast<int>(std::min<uint64_t>(args.num_tiles, resident)), C::THREADS, L::total, st>>>(args);
+            return cudaGetLastError();
+        }
+        if (pass_gen == 4) {   // rs_pass4.cuh: the first generation with its shared-memory accesses un-serialised
+            using L = Pass4Smem<KeyT, HAS_VALS, C::THREADS, C::KPT>;
+            auto kern = rs_pass4_kernel<KeyT, HAS_VALS, C::THREADS, C::KPT, C::MINB, FK>;
+            static thread_local PassLaunchState state;
+            cudaError_t e = configure_pass(kern, ctx->device, C::THREADS, L::total, state, &blocks_per_sm);
+            if (e != cudaSuccess) return e;
+            const uint64_t resident = static_cast<uint64_t>(blocks_per_sm) * ctx->sm_count;
+            kern<<<static_cast<int>(std::min<uint64_t>(args.num_tiles, resident)), C::THREADS, L::total, st>>>(args);
+            return cudaGetLastError();
+        }
+#endif
+        static const bool sweep_v2 = std::getenv("RSB200_SWEEP_V2") != nullptr || pass_gen == 2;
         if (sweep_v2) {
             using L = SweepSmem<KeyT, HAS_VALS, C::THREADS, C::KPT>;
             auto kern = rs_sweep_kernel<KeyT, HAS_VALS, C::THREADS, C::KPT, C::MINB, FK>;
