@@ -171,7 +171,7 @@ struct TileCfg;
 // atomic ranking mode (default on B200): larger tiles pay (fewer look-backs and table scans per key)
 #ifndef RS_U32A_THREADS
 #define RS_U32A_THREADS 512
-#define RS_U32A_KPT 22
+#define RS_U32A_KPT 23
 #define RS_U32A_MINB 2
 #endif
 #ifndef RS_U32VA_THREADS

@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 $CMD > gpurun_out/${TAG}_bench_plain.json 2> gpurun_out/${TAG}_bench_plain.err || { echo "plain bench failed"; tail -5 gpurun_out/${TAG}_bench_plain.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
 echo "launch list rc=$?"
-# warm-up sort = launches hist, scan, 4 passes; capture the second sort's histogram + first two passes
-ncu --set full --clock-control none --import-source on -k regex:"onesweep|histogram" -s 5 -c 3 -o gpurun_out/${TAG}_full $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
+# 14 matching launches belong to the self-test sorts of rs_context_create, 5 to the first warm-up sort: capture the second warm-up sort (histogram + 4 passes)
+ncu --set full --clock-control none --import-source on -k regex:"onesweep|histogram" -s 19 -c 5 -o gpurun_out/${TAG}_full $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "full capture rc=$?"
 ls -la gpurun_out | tail -8
