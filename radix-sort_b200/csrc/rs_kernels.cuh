@@ -53,21 +53,6 @@ constexpr int      MAX_PASSES        = 8;
 #endif
 constexpr int      LB_WINDOW         = RS_LB_WINDOW;  // look-back status words in flight per thread
 constexpr unsigned long long BASE_READY = 1ull << 63;      // ready flag of a chunk-base word
-// A/B switches of the default pass kernel (tools/build_variants.sh; see profiles/README.md for what each measured):
-//   RS_X_LBTIGHT 1: branch-free evaluation of a look-back window (selects instead of a chain of early exits)
-//   RS_X_CBASE   1: the chunk base of a digit is polled once per chunk and cached in shared memory
-//   RS_X_COUNT   0: rows of 32 equal digits are found in the count phase and counted by one lane;
-//                1: every lane counts itself (ATOMS.POPC.INC merges equal addresses), uniform rows are found while scattering;
-//                2: no uniform-row handling at all (measurement only: degenerate inputs serialise)
-#ifndef RS_X_LBTIGHT
-#define RS_X_LBTIGHT 0
-#endif
-#ifndef RS_X_CBASE
-#define RS_X_CBASE 1
-#endif
-#ifndef RS_X_COUNT
-#define RS_X_COUNT 0
-#endif
 
 // Per-sort plan written by rs_scan_kernel: a pass whose digit is the same for every key is the identity
 // (stable sort on a constant digit) and is skipped on the device, without a host round trip.  The
@@ -490,8 +475,8 @@ struct OnesweepSmem {
     static constexpr size_t off_wsum    = off_ptot_own + (PTOT_IN_KPTR ? 0 : sizeof(uint32_t) * PARTS * RADIX);
     static constexpr size_t off_mbar    = off_wsum + sizeof(uint32_t) * 16;
     static constexpr size_t off_tile    = off_mbar + sizeof(uint64_t) * 2;
-    static constexpr size_t off_cbase   = off_tile + sizeof(uint32_t) * 4;   // RS_X_CBASE: [digit] (chunk + 1) << 48 | chunk base
-    static constexpr size_t total       = off_cbase + (RS_X_CBASE ? sizeof(unsigned long long) * RADIX : 0);
+    static constexpr size_t off_cbase   = off_tile + sizeof(uint32_t) * 4;   // [digit] (chunk + 1) << 48 | cached chunk base
+    static constexpr size_t total       = off_cbase + sizeof(unsigned long long) * RADIX;
 };
 
 __device__ __forceinline__ uint32_t atoms_add_return(uint32_t* p, uint32_t v) {
@@ -545,7 +530,7 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
     uint32_t* const    wsum    = reinterpret_cast<uint32_t*>(smem_raw + L::off_wsum);
     uint64_t* const    mbar    = reinterpret_cast<uint64_t*>(smem_raw + L::off_mbar);
     volatile uint32_t* sh_tile = reinterpret_cast<volatile uint32_t*>(smem_raw + L::off_tile);
-    unsigned long long* const cbase = reinterpret_cast<unsigned long long*>(smem_raw + L::off_cbase);  // RS_X_CBASE only
+    unsigned long long* const cbase = reinterpret_cast<unsigned long long*>(smem_raw + L::off_cbase);
 
     const int       tid   = threadIdx.x;
     const int       lane  = tid & 31;
@@ -581,7 +566,7 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
     // the tables start clean; every tile re-zeroes them itself after its scatter
 #pragma unroll
     for (int j = 0; j < GPP; ++j) tab[(sp * GPP + j) * RADIX + sd] = 0u;
-    if constexpr (RS_X_CBASE != 0) { if (sp == 0) cbase[sd] = 0ull; }   // tag 0: nothing cached
+    if (sp == 0) cbase[sd] = 0ull;   // tag 0: nothing cached
     __syncthreads();
 
     uint32_t phase_bits = 0;  // bit s = parity to wait for on mbar[s]
@@ -626,9 +611,7 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
         for (int r = 0; r < KPT; ++r) {
             uint32_t d = digit_of<FK>(key[r], ds);
             if (!FULL && (my_first + ROW * r) >= valid) d = RADIX - 1;  // padding ranks last
-            if constexpr (ATOMIC_RANK && RS_X_COUNT != 0) {
-                atomicAdd(&gt[d], 1u);
-            } else if constexpr (ATOMIC_RANK) {
+            if constexpr (ATOMIC_RANK) {
                 int all_same;
                 __match_all_sync(0xffffffffu, d, &all_same);
                 if (all_same) {  // 32 equal digits would serialise on one word: one lane counts them all
@@ -714,14 +697,7 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
                 // gt[d] is the running tile position of (this warp, digit d).  Lanes that hit the same word are served
                 // in ascending lane order (self-tested, see the header comment), so the returned value is the stable
                 // position of this key.
-                bool uni = (uniform_rows >> r) & 1u;
-                if constexpr (RS_X_COUNT == 1) {
-                    int all_same;
-                    __match_all_sync(0xffffffffu, d, &all_same);
-                    uni = all_same != 0;
-                }
-                if constexpr (RS_X_COUNT == 2) uni = false;
-                if (uni) {
+                if (uniform_rows & (1u << r)) {
                     uint32_t c = 0;
                     if (lane == 0) c = atoms_add_return(&gt[d], 32u);
                     pos = __shfl_sync(0xffffffffu, c, 0) + lane;
@@ -749,35 +725,15 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
 #pragma unroll
                     for (int j = 0; j < LB_WINDOW; ++j)
                         v[j] = (j < left) ? ld_status(p - j * RADIX) : STATUS_INCLUSIVE;  // before the chunk: prefix 0
-                    if constexpr (RS_X_LBTIGHT != 0) {
-                        // the published prefix of the window, up to and including the first inclusive word, without
-                        // branches: this loop is on the critical path of the whole launch (every tile's inclusive
-                        // prefix waits for a predecessor's)
-                        uint32_t sum = 0, taken = 0;
-                        bool     open = true;
 #pragma unroll
-                        for (int j = 0; j < LB_WINDOW; ++j) {
-                            const uint32_t f    = v[j] >> 30;
-                            const bool     take = open && f != 0;
-                            sum   += take ? (v[j] & STATUS_VALUE_MASK) : 0u;
-                            taken += take ? 1u : 0u;
-                            done   = done || (take && f == 2);
-                            open   = take && f != 2;
-                        }
-                        excl += sum;
-                        p    -= static_cast<size_t>(taken) * RADIX;
-                        left -= static_cast<int32_t>(taken);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < LB_WINDOW; ++j) {
-                            if (done) break;
-                            const uint32_t f = v[j] >> 30;
-                            if (f == 0) break;  // not published yet: re-read from here
-                            excl += v[j] & STATUS_VALUE_MASK;
-                            p -= RADIX;
-                            --left;
-                            if (f == 2) done = true;
-                        }
+                    for (int j = 0; j < LB_WINDOW; ++j) {
+                        if (done) break;
+                        const uint32_t f = v[j] >> 30;
+                        if (f == 0) break;  // not published yet: re-read from here
+                        excl += v[j] & STATUS_VALUE_MASK;
+                        p -= RADIX;
+                        --left;
+                        if (f == 2) done = true;
                     }
                 }
                 RS_DCHECK(excl + count <= CHUNK_MAX_KEYS);
@@ -785,19 +741,15 @@ rs_onesweep_kernel(const OnesweepArgs<KeyT> a) {
             }
             // global offset of this chunk's first key with this digit (ready at once for chunk 0)
             unsigned long long* cb_ptr = a.base + static_cast<size_t>(chunk) * RADIX + sd;
-            unsigned long long  cb;
-            if constexpr (RS_X_CBASE != 0) {
-                cb = cbase[sd];   // the thread that owns the digit is the only one that touches its slot
-                if ((cb >> 48) == chunk + 1) {
-                    cb &= (1ull << 48) - 1;
-                } else {
-                    do { cb = ld_base(cb_ptr); } while (!(cb & BASE_READY));
-                    cb &= ~BASE_READY;
-                    cbase[sd] = cb | (static_cast<unsigned long long>(chunk + 1) << 48);
-                }
+            // polled once per chunk and digit, then cached in shared memory (the thread that owns the digit is the only
+            // one that touches its slot): one L2 round trip less between the look-back and barrier (D), -1 % per pass
+            unsigned long long  cb = cbase[sd];
+            if ((cb >> 48) == chunk + 1) {
+                cb &= (1ull << 48) - 1;
             } else {
                 do { cb = ld_base(cb_ptr); } while (!(cb & BASE_READY));
                 cb &= ~BASE_READY;
+                cbase[sd] = cb | (static_cast<unsigned long long>(chunk + 1) << 48);
             }
             // the last tile of a chunk hands the next chunk its base (its inclusive prefix = the chunk's counts)
             if ((t % a.tiles_per_chunk) == a.tiles_per_chunk - 1 && chunk + 1 < a.num_chunks)
