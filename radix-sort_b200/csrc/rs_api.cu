@@ -192,7 +192,7 @@ struct TileCfg;
 template <> struct TileCfg<uint32_t, false, false> { static constexpr int THREADS = RS_U32_THREADS, KPT = RS_U32_KPT, MINB = RS_U32_MINB; };
 template <> struct TileCfg<uint32_t, true,  false> { static constexpr int THREADS = 512, KPT = 12, MINB = 2; };
 template <> struct TileCfg<uint64_t, false, false> { static constexpr int THREADS = 512, KPT = 8,  MINB = 2; };
-template <> struct TileCfg<uint64_t, true,  false> { static constexpr int THREADS = 512, KPT = 8,  MINB = 2; };
+template <> struct TileCfg<uint64_t, true,  false> { static constexpr int THREADS = 512, KPT = 7,  MINB = 2; };  // 8 keys left room for ONE CTA per SM (found by the static_assert in launch_pass_mode)
 template <> struct TileCfg<uint32_t, false, true>  { static constexpr int THREADS = RS_U32A_THREADS, KPT = RS_U32A_KPT, MINB = RS_U32A_MINB; };
 template <> struct TileCfg<uint32_t, true,  true>  { static constexpr int THREADS = RS_U32VA_THREADS, KPT = RS_U32VA_KPT, MINB = RS_U32VA_MINB; };
 template <> struct TileCfg<uint64_t, false, true>  { static constexpr int THREADS = RS_U64A_THREADS, KPT = RS_U64A_KPT, MINB = RS_U64A_MINB; };
@@ -402,6 +402,9 @@ static cudaError_t launch_pass_mode(rs_context ctx, cudaStream_t st, const Onesw
     }
     {
         using L = OnesweepSmem<KeyT, HAS_VALS, C::THREADS, C::KPT, ATOMIC>;
+        // sm_100: 228 KiB of shared memory per SM, 1 KiB of it reserved per resident CTA -- a tile shape that does not
+        // leave room for C::MINB CTAs would silently halve the occupancy the kernel was tuned for
+        static_assert(L::total <= (228u * 1024u - 1024u * C::MINB) / C::MINB, "tile shape does not fit MINB CTAs per SM");
         auto kern = rs_onesweep_kernel<KeyT, HAS_VALS, C::THREADS, C::KPT, C::MINB, ATOMIC, FK>;
         static thread_local PassLaunchState state;
         cudaError_t e = configure_pass(kern, ctx->device, C::THREADS, L::total, state, &blocks_per_sm);
