@@ -187,7 +187,8 @@ constexpr int HIST_VECS    = 4;  // 16-byte vectors in flight per thread
 template <int NPASS>
 struct HistCfg {
     static constexpr int    COLS  = NPASS <= 4 ? 32 : 16;
-    static constexpr size_t bytes = sizeof(uint32_t) * NPASS * RADIX * COLS;
+    // more than four passes (8-byte keys): the split layout of the byte-digit path is [4][256][32] whatever NPASS is
+    static constexpr size_t bytes = NPASS <= 4 ? sizeof(uint32_t) * NPASS * RADIX * COLS : sizeof(uint32_t) * 4 * RADIX * 32;
 };
 
 template <typename KeyT, int NPASS, bool FK>
@@ -196,16 +197,77 @@ rs_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long lon
                     PassTable pt, int byte_digits, KeyT key_flip) {
     constexpr int KV   = 16 / sizeof(KeyT);
     constexpr int COLS = HistCfg<NPASS>::COLS;
-    extern __shared__ __align__(16) uint32_t hist_sh[];  // [NPASS][256][COLS]
+    extern __shared__ __align__(16) uint32_t hist_sh[];  // [NPASS][256][COLS]  (SPLIT: [4][256][32], see below)
     const int      tid     = threadIdx.x;
     const int      lane    = tid & 31;
     const uint32_t col     = lane & (COLS - 1);
     const bool     aligned = (reinterpret_cast<uintptr_t>(keys) & 15u) == 0;
 
-    for (int i = tid; i < NPASS * RADIX * COLS; i += HIST_THREADS) hist_sh[i] = 0;
+    for (int i = tid; i < static_cast<int>(HistCfg<NPASS>::bytes / sizeof(uint32_t)); i += HIST_THREADS) hist_sh[i] = 0;
     __syncthreads();
     const uint64_t nvec = aligned ? n / KV : 0;
     const uint4*   cv   = reinterpret_cast<const uint4*>(keys);
+
+    // SPLIT (8-byte keys, more than four byte digits): 32 columns per digit row do not fit for eight passes, and with 16
+    // two lanes share a column (every atomic two wavefronts: 0.62 ms for 2 GiB, LSU-bound).  Instead the two half-warps
+    // read the SAME keys; lanes 0-15 count bytes 0-3 (the low word), lanes 16-31 bytes 4-7 (the high word), into
+    // [4][256][32] where columns 0-15 of row (q, d) belong to pass q and columns 16-31 to pass q + 4.  The bank of an
+    // access is the lane again: one wavefront per atomic, half as many atomics per lane.
+    constexpr bool CAN_SPLIT = sizeof(KeyT) == 8 && NPASS > 4;
+    if (CAN_SPLIT && byte_digits) {
+        if constexpr (CAN_SPLIT) {
+            const int      half     = lane >> 4;
+            const uint32_t col_bits = static_cast<uint32_t>(lane) << 2;
+            const int      my_npass = half ? NPASS - 4 : 4;       // byte digits this lane counts
+            auto count_word = [&](KeyT k) {
+                if constexpr (FK) k = float_order_bits(k, pt.d[0].finf); else k ^= key_flip;
+                const uint32_t w = half ? static_cast<uint32_t>(static_cast<unsigned long long>(k) >> 32) : static_cast<uint32_t>(k);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (q < my_npass) {
+                        uint32_t off = (8 * q >= 7) ? (w >> (8 * q - 7)) : (w << (7 - 8 * q));
+                        off = (off & (0xffu << 7)) | col_bits;
+                        atomicAdd(reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(hist_sh) + q * RADIX * 32 * sizeof(uint32_t) + off), 1u);
+                    }
+                }
+            };
+            // both half-warps walk the same vectors: 512 logical threads per block
+            const uint32_t ltid   = static_cast<uint32_t>(tid >> 5) * 16 + (lane & 15);
+            const uint64_t stride = static_cast<uint64_t>(gridDim.x) * (HIST_THREADS / 2);
+            const uint64_t first  = static_cast<uint64_t>(blockIdx.x) * (HIST_THREADS / 2) + ltid;
+            for (uint64_t base = first; base < nvec; base += stride * HIST_VECS) {
+                uint4 v[HIST_VECS];
+                bool  act[HIST_VECS];
+#pragma unroll
+                for (int u = 0; u < HIST_VECS; ++u) {
+                    const uint64_t idx = base + u * stride;
+                    act[u]             = idx < nvec;
+                    v[u]               = act[u] ? __ldg(cv + idx) : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < HIST_VECS; ++u) {
+                    if (!act[u]) continue;
+                    count_word(static_cast<KeyT>((static_cast<uint64_t>(v[u].y) << 32) | v[u].x));
+                    count_word(static_cast<KeyT>((static_cast<uint64_t>(v[u].w) << 32) | v[u].z));
+                }
+            }
+            for (uint64_t i = nvec * KV + first; i < n; i += stride) count_word(keys[i]);
+            __syncthreads();
+            // fold: row (q, d) -> pass q from columns 0-15, pass q + 4 from columns 16-31 (rotated by the lane: 32 banks)
+            for (int row = tid; row < 4 * RADIX; row += HIST_THREADS) {
+                unsigned long long lo = 0, hi = 0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int c = (j + lane) & 15;
+                    lo += hist_sh[row * 32 + c];
+                    hi += hist_sh[row * 32 + 16 + c];
+                }
+                if (lo) atomicAdd(&hist[row], lo);
+                if (hi && row + 4 * RADIX < NPASS * RADIX) atomicAdd(&hist[row + 4 * RADIX], hi);
+            }
+        }
+        return;
+    }
 
     // byte_digits (the usual whole-key sort: digit p is byte p of the key, key_flip = the sign bit of signed keys): the
     // key is put into unsigned order ONCE, and the byte offset of a counter -- digit * COLS * 4 + col * 4 -- costs one
