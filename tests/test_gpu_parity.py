@@ -265,7 +265,10 @@ def test_sort_device_bit_ranges(rsb, gpu, oracle, t):
     vbufs = [torch.empty_like(vin), torch.empty_like(vin)]
     torch.cuda.synchronize()
     u = data.view(np.uint32 if data.itemsize == 4 else np.uint64)
-    for b, e in ((0, bits), (0, 8), (4, 13), (bits - 11, bits), (3, bits - 5), (8, 24)):
+    ranges = ((0, bits), (0, 8), (4, 13), (bits - 11, bits), (3, bits - 5), (8, 24))
+    if bits == 64:   # five and seven whole-byte digits from bit 0: the split-half histogram with a partly idle upper half
+        ranges += ((0, 40), (0, 56))
+    for b, e in ranges:
         r = s.sort_device(st, d_in.data_ptr(), bufs[0].data_ptr(), bufs[1].data_ptr(), n, vin.data_ptr(),
                           vbufs[0].data_ptr(), vbufs[1].data_ptr(), begin_bit=b, end_bit=e)
         st.sync()
