@@ -1125,6 +1125,22 @@ int rs_sorter_pad(rs_sorter s, rs_stream st, uint64_t first_key, uint64_t rounde
     return RS_OK;
 }
 
+// Host <-> device copies go out in pieces of 128 MiB (RSB200_COPY_CHUNK_MIB overrides, 0 = one cudaMemcpyAsync).  With an
+// upload and a download in flight on two streams one host of this pool moved 35 GB/s each way with whole-GiB copies and
+// 44 GB/s with 128 MiB pieces; others move 44-48 GB/s either way (tools/pcie_probe.py, tools/e2e_probe.py,
+// profiles/r2_pcie_probe.txt) -- pieces never measured slower.
+static cudaError_t copy_in_pieces(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
+    const char* e = std::getenv("RSB200_COPY_CHUNK_MIB");
+    const size_t piece = (e ? static_cast<size_t>(std::atol(e)) : size_t{128}) << 20;
+    if (piece == 0 || bytes <= piece) return cudaMemcpyAsync(dst, src, bytes, kind, st);
+    for (size_t off = 0; off < bytes; off += piece) {
+        const size_t len = std::min(piece, bytes - off);
+        cudaError_t err = cudaMemcpyAsync(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len, kind, st);
+        if (err != cudaSuccess) return err;
+    }
+    return cudaSuccess;
+}
+
 int rs_sorter_upload(rs_sorter s, rs_stream st, const void* h_keys, const uint32_t* h_perm, uint64_t n) {
     if (!s || !st) return fail(RS_DATA_UPLOAD_FAILED, "null argument");
     if (!s->keys[0]) return fail(RS_DATA_UPLOAD_FAILED, "sorter has no key buffers");
@@ -1132,10 +1148,10 @@ int rs_sorter_upload(rs_sorter s, rs_stream st, const void* h_keys, const uint32
     if (n && !h_keys) return fail(RS_HOST_BUFFERS_FAILED, "null host key buffer");
     DeviceGuard guard(s->ctx->device); if (guard.status != cudaSuccess) return fail(RS_DATA_UPLOAD_FAILED, "cudaSetDevice", guard.status);
     if (n == 0) return RS_OK;
-    RS_CUDA(cudaMemcpyAsync(s->keys[0], h_keys, n * s->key_bytes, cudaMemcpyHostToDevice, st->st), RS_DATA_UPLOAD_FAILED);
+    RS_CUDA(copy_in_pieces(s->keys[0], h_keys, n * s->key_bytes, cudaMemcpyHostToDevice, st->st), RS_DATA_UPLOAD_FAILED);
     if (s->has_vals) {
         if (h_perm) {
-            RS_CUDA(cudaMemcpyAsync(s->vals[0], h_perm, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st->st),
+            RS_CUDA(copy_in_pieces(s->vals[0], h_perm, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st->st),
                     RS_DATA_UPLOAD_FAILED);
         } else {
             rs_iota_kernel<<<grid_for(n, 256, s->ctx->sm_count), 256, 0, st->st>>>(s->vals[0], n);
@@ -1304,11 +1320,11 @@ int rs_sorter_download_async(rs_sorter s, rs_stream st, void* h_keys_out, uint32
     DeviceGuard guard(s->ctx->device); if (guard.status != cudaSuccess) return fail(RS_DATA_DOWNLOAD_FAILED, "cudaSetDevice", guard.status);
     const int r = s->result_index;
     if (n && h_keys_out)
-        RS_CUDA(cudaMemcpyAsync(h_keys_out, s->keys[r], n * s->key_bytes, cudaMemcpyDeviceToHost, st->st),
+        RS_CUDA(copy_in_pieces(h_keys_out, s->keys[r], n * s->key_bytes, cudaMemcpyDeviceToHost, st->st),
                 RS_DATA_DOWNLOAD_FAILED);
     if (n && h_perm_out) {
         if (!s->has_vals) return fail(RS_DATA_DOWNLOAD_FAILED, "sorter was created without RS_WITH_PERMUTATION");
-        RS_CUDA(cudaMemcpyAsync(h_perm_out, s->vals[r], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st->st),
+        RS_CUDA(copy_in_pieces(h_perm_out, s->vals[r], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st->st),
                 RS_DATA_DOWNLOAD_FAILED);
     }
     return RS_OK;

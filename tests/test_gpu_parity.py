@@ -1,5 +1,6 @@
 """GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the oracle, the
 committed golden vectors and numpy (= std::sort / std::stable_sort argsort), bit-exact."""
+import os
 import numpy as np
 import pytest
 
@@ -729,8 +730,11 @@ def test_pinned_async_lanes_bit_exact(rsb, gpu, oracle, t, with_perm):
             _assert_stable_permutation(inputs[b], got, lane["hperm"].array)
         got[:] = 0                             # a stale buffer must not pass for the next batch
 
+    old_piece = os.environ.get("RSB200_COPY_CHUNK_MIB")
     try:
         for b in range(batches):
+            # host copies in 1 MiB pieces, whole, and in the default 128 MiB pieces (read by the library per call)
+            os.environ["RSB200_COPY_CHUNK_MIB"] = ("1", "0", "128")[b % 3]
             lane = lanes[b % lanes_n]
             verify(lane)
             lane["hin"].array[:] = inputs[b]
@@ -741,6 +745,10 @@ def test_pinned_async_lanes_bit_exact(rsb, gpu, oracle, t, with_perm):
         for lane in lanes:
             verify(lane)
     finally:
+        if old_piece is None:
+            os.environ.pop("RSB200_COPY_CHUNK_MIB", None)
+        else:
+            os.environ["RSB200_COPY_CHUNK_MIB"] = old_piece
         for lane in lanes:
             lane["s"].close(); lane["st"].close(); lane["hin"].close(); lane["hout"].close()
             if lane["hperm"] is not None:
