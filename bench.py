@@ -327,7 +327,7 @@ def bench_single(args):
     e2e = {"value": n / e2e_ms / 1e6, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
            "h2d_bytes_per_step": n * KEY_BYTES, "d2h_bytes_per_step": n * KEY_BYTES,
            "api": "rs_sorter_upload -> rs_sorter_sort -> rs_sorter_download_async on three sorters/streams "
-                  "(batch i+2 uploads while batch i+1 sorts and batch i downloads), pinned host buffers",
+                  "(batch i+2 uploads while batch i+1 sorts and batch i downloads), pinned host buffers, copies issued in 128 MiB pieces",
            "timing": "host wall clock between device synchronisations",
            "verified": "each lane's downloaded buffer: sorted, and multiset fingerprint equal to the host input's",
            "input": "every step uploads the same pinned 1 GiB host buffer (the workload), and downloads 1 GiB",
