@@ -23,6 +23,11 @@
 // Stability rests on the same hardware property as before: lanes of ONE warp instruction that hit the same shared
 // word are served in ascending lane order (self-tested per context, see rs_api.cu).
 // Algorithmic traffic: sizeof(KeyT) read + sizeof(KeyT) written per key (+4 +4 with the index payload).
+//
+// RESULT (profiles/README.md, profiles/r2_pass_v1_vs_v3_ncu.txt, round 2): 14 % fewer shared-memory wavefronts, yet
+// 0.729 ms per pass against 0.678 of the first generation (0.79 with the batched atomics that are in this file now):
+// the loads cost 1.8 wavefronts per 32 keys in the global half of the same pipe, plus issue slots and MIO-queue stalls.
+// Kept as the record of that experiment, compiled with -DRS_EXPERIMENTAL_PASSES only.
 #pragma once
 #include "rs_kernels.cuh"
 

@@ -22,6 +22,11 @@
 // Stability rests on the same hardware property as before: lanes of ONE warp instruction that hit the same shared
 // word are served in ascending lane order (self-tested per context, see rs_api.cu).
 // Algorithmic traffic: sizeof(KeyT) read + sizeof(KeyT) written per key (+4 +4 with the index payload).
+//
+// RESULT (profiles/README.md, round 2): 0.741-0.744 ms per pass against 0.678 of the first generation, whatever the batch
+// size -- kept as the record of that experiment, compiled with -DRS_EXPERIMENTAL_PASSES only.  It was measured with
+// 512 x 22-key tiles (build with -DRS_U32A_KPT=22 to repeat it): its 2 KB larger shared-memory layout leaves room for
+// only one CTA per SM with the 512 x 23 tiles the default kernel uses since.
 #pragma once
 #include "rs_kernels.cuh"
 #include "rs_pass3.cuh"   // forget_derived
